@@ -1,0 +1,554 @@
+// engine.cu -- host side of the B200 stereo depth engine and its C ABI (include/ss_b200.h).
+//
+// Replaces simsense::DepthSensorEngine's host code (3rd_party/simsense/src/core.cu:65-787):
+// buffer ownership, stage sequencing, getters/setters.  Differences by design: bound to an
+// explicit device; one stream + one helper stream with event fork/join instead of 3 streams and
+// 13-16 cudaDeviceSynchronize per frame; status codes instead of exit(); a batch dimension; 3-4
+// resident cost volumes instead of 7.
+#include "../../include/ss_b200.h"
+#include "kernels.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace ssb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t _e = (call);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return fail(SS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));               \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int census_bits(int cw, int ch) {
+  const int bits = ((ch - 1) / 2) * cw + cw / 2;
+  return std::min(bits, 32);
+}
+
+// Ranges of python/py_package/sensor/simsense_component.py:54-134.
+int validate_params(const ss_config &c) {
+  if (c.rows < 32 || c.cols < 32) return fail(SS_ERR_INVALID, "Infrared resolution (width and height) must be integer and no less than 32");
+  if (c.census_width <= 0 || c.census_height <= 0 || c.census_width % 2 == 0 || c.census_height % 2 == 0 || c.census_width * c.census_height > 65)
+    return fail(SS_ERR_INVALID, "census_width and census_height must be positive odd integers and their product should be no larger than 65");
+  if (c.max_disp < 32 || c.max_disp > 1024) return fail(SS_ERR_INVALID, "max_disp must be integer and within range [32, 1024]");
+  if (c.bf_width <= 0 || c.bf_height <= 0 || c.bf_width % 2 == 0 || c.bf_height % 2 == 0 || c.bf_width * c.bf_height > 256)
+    return fail(SS_ERR_INVALID, "block_width and block_height must be positive odd integers and their product should be no larger than 256");
+  if (c.bf_width / 2 >= (int)c.cols || c.bf_height / 2 >= (int)c.rows) return fail(SS_ERR_INVALID, "matching block larger than the image");
+  if (c.p1 <= 0 || c.p2 <= 0 || c.p1 >= c.p2 || c.p2 >= 224)
+    return fail(SS_ERR_INVALID, "p1_penalty must be positive integer less than p2_penalty and p2_penalty be positive integer less than 224");
+  if (c.uniq_ratio < 0 || c.uniq_ratio > 255) return fail(SS_ERR_INVALID, "uniqueness_ratio must be positive integer and no larger than 255");
+  if (c.lr_max_diff < -1 || c.lr_max_diff > 255) return fail(SS_ERR_INVALID, "lr_max_diff must be integer and within the range [0, 255]");
+  if (c.mf_size != 1 && c.mf_size != 3 && c.mf_size != 5 && c.mf_size != 7) return fail(SS_ERR_INVALID, "Median filter size choices are 1, 3, 5, 7");
+  return SS_OK;
+}
+
+} // namespace
+
+struct ss_engine {
+  ss_config cfg{};
+  int device = 0;
+  cudaStream_t stream = nullptr, aux = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  std::vector<void *> allocs;
+  float *mapLx = nullptr, *mapLy = nullptr, *mapRx = nullptr, *mapRy = nullptr;
+  float *a1 = nullptr, *a2 = nullptr, *a3 = nullptr;
+  uint8_t *raw0 = nullptr, *raw1 = nullptr, *im0 = nullptr, *im1 = nullptr;
+  uint32_t *cen0 = nullptr, *cen1 = nullptr;
+  uint16_t *C = nullptr, *L1 = nullptr, *L2 = nullptr, *S3 = nullptr;
+  uint16_t *dbgL0 = nullptr, *dbgL3 = nullptr, *dbgLAll = nullptr;
+  float *dispL = nullptr, *disp_lr = nullptr, *disp_med = nullptr, *disp_full = nullptr;
+  float *depth = nullptr, *canvas = nullptr, *out = nullptr, *pc = nullptr, *rgbpc = nullptr;
+  uint16_t *dispR = nullptr;
+  int wave = 1;
+  bool computed = false;
+  int mrows = 0, mcols = 0; // matched size of the last compute
+  uint64_t frame = 0;
+  int launches = 0;
+  // profiling
+  bool profiling = false;
+  std::vector<cudaEvent_t> pev;
+  std::vector<const char *> pnames;
+  std::vector<float> ptimes;
+
+  size_t fsz() const { return (size_t)cfg.rows * cfg.cols; }
+  size_t rsz() const { return cfg.registration ? (size_t)cfg.rgb_rows * cfg.rgb_cols : fsz(); }
+  uint32_t out_rows() const { return cfg.registration ? cfg.rgb_rows : cfg.rows; }
+  uint32_t out_cols() const { return cfg.registration ? cfg.rgb_cols : cfg.cols; }
+
+  template <class T> int alloc(T **p, size_t count) {
+    void *q = nullptr;
+    CK(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    allocs.push_back(q);
+    *p = static_cast<T *>(q);
+    return SS_OK;
+  }
+  int ensure_generic_volumes() {
+    const size_t v = (size_t)wave * fsz() * cfg.max_disp;
+    if (!dbgL0) { int r = alloc(&dbgL0, v); if (r) return r; }
+    if (!dbgL3) { int r = alloc(&dbgL3, v); if (r) return r; }
+    if (!dbgLAll) { int r = alloc(&dbgLAll, v); if (r) return r; }
+    return SS_OK;
+  }
+  void mark(const char *name) {
+    if (!profiling) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, stream);
+    pev.push_back(e);
+    pnames.push_back(name);
+  }
+};
+
+namespace {
+
+int upload(ss_engine *e, float **dst, const float *src, size_t n) {
+  int r = e->alloc(dst, n);
+  if (r) return r;
+  CK(cudaMemcpyAsync(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  return SS_OK;
+}
+
+int create_impl(ss_engine *e, const float *mapLx, const float *mapLy, const float *mapRx,
+                const float *mapRy, const float *a1, const float *a2, const float *a3) {
+  const ss_config &c = e->cfg;
+  CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking));
+  for (auto &ev : e->ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
+  const size_t fsz = e->fsz(), N = (size_t)c.batch;
+  int r;
+  if (!c.rectified) {
+    if (!mapLx || !mapLy || !mapRx || !mapRy) return fail(SS_ERR_INVALID, "rectification maps required when rectified is false");
+    if ((r = upload(e, &e->mapLx, mapLx, fsz))) return r;
+    if ((r = upload(e, &e->mapLy, mapLy, fsz))) return r;
+    if ((r = upload(e, &e->mapRx, mapRx, fsz))) return r;
+    if ((r = upload(e, &e->mapRy, mapRy, fsz))) return r;
+  }
+  if (c.registration) {
+    if (!a1 || !a2 || !a3) return fail(SS_ERR_INVALID, "registration planes a1,a2,a3 required");
+    if ((r = upload(e, &e->a1, a1, fsz))) return r;
+    if ((r = upload(e, &e->a2, a2, fsz))) return r;
+    if ((r = upload(e, &e->a3, a3, fsz))) return r;
+  }
+  // cost volumes: C, L1, L2 (S3 aliases L2) -- or 7 separate ones with keep_stages
+  const size_t vol = fsz * (size_t)c.max_disp * sizeof(uint16_t);
+  const int nvol = c.keep_stages ? 7 : 3;
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  const size_t small = N * (fsz * 40 + e->rsz() * 48) + (64u << 20);
+  if (free_b < small + (size_t)nvol * vol) return fail(SS_ERR_CUDA, "not enough device memory for one frame");
+  size_t budget = (size_t)((double)(free_b - small) * 0.6);
+  e->wave = (int)std::min<size_t>(N, std::max<size_t>(1, budget / ((size_t)nvol * vol)));
+  const size_t wv = (size_t)e->wave * fsz * c.max_disp;
+  if ((r = e->alloc(&e->C, wv))) return r;
+  if ((r = e->alloc(&e->L1, wv))) return r;
+  if ((r = e->alloc(&e->L2, wv))) return r;
+  if (c.keep_stages) {
+    if ((r = e->alloc(&e->S3, wv))) return r;
+    if ((r = e->ensure_generic_volumes())) return r;
+  } else {
+    e->S3 = e->L2;
+  }
+  if ((r = e->alloc(&e->raw0, N * fsz))) return r;
+  if ((r = e->alloc(&e->raw1, N * fsz))) return r;
+  if ((r = e->alloc(&e->im0, N * fsz))) return r;
+  if ((r = e->alloc(&e->im1, N * fsz))) return r;
+  if ((r = e->alloc(&e->cen0, N * fsz))) return r;
+  if ((r = e->alloc(&e->cen1, N * fsz))) return r;
+  if ((r = e->alloc(&e->dispL, N * fsz))) return r;
+  if ((r = e->alloc(&e->dispR, N * fsz))) return r;
+  if ((r = e->alloc(&e->disp_lr, N * fsz))) return r;
+  if ((r = e->alloc(&e->disp_med, N * fsz))) return r;
+  if ((r = e->alloc(&e->disp_full, N * fsz))) return r;
+  if ((r = e->alloc(&e->depth, N * fsz))) return r;
+  if (c.registration && (r = e->alloc(&e->canvas, N * e->rsz()))) return r;
+  if ((r = e->alloc(&e->out, N * e->rsz()))) return r;
+  if ((r = e->alloc(&e->pc, N * e->rsz() * 3))) return r;
+  if ((r = e->alloc(&e->rgbpc, N * e->rsz() * 6))) return r;
+  CK(cudaStreamSynchronize(e->stream));
+  return SS_OK;
+}
+
+enum InputKind { IN_U8, IN_RGBA };
+
+int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *right,
+                 const ss_bbox *bbox, cudaStream_t user) {
+  const ss_config &c = e->cfg;
+  if (!left || !right) return fail(SS_ERR_INVALID, "null input image");
+  int bx = 0, by = 0, rows = (int)c.rows, cols = (int)c.cols, use_bbox = 0;
+  if (bbox && bbox->enabled) {
+    if (bbox->width < 1 || bbox->height < 1 || (uint64_t)bbox->x + bbox->width > c.cols ||
+        (uint64_t)bbox->y + bbox->height > c.rows)
+      return fail(SS_ERR_INVALID, "bbox must be non-empty and inside the image");
+    if (c.bf_width / 2 >= (int)bbox->width || c.bf_height / 2 >= (int)bbox->height)
+      return fail(SS_ERR_INVALID, "bbox smaller than the matching block");
+    bx = (int)bbox->x; by = (int)bbox->y; cols = (int)bbox->width; rows = (int)bbox->height;
+    use_bbox = 1;
+  }
+  e->computed = false;
+  cudaStream_t st = e->stream;
+  if (user && user != st) { // order after the caller's stream
+    CK(cudaEventRecord(e->ev_in, user));
+    CK(cudaStreamWaitEvent(st, e->ev_in, 0));
+  }
+  for (auto ev : e->pev) cudaEventDestroy(ev);
+  e->pev.clear(); e->pnames.clear();
+  e->mark("begin");
+
+  const int D = c.max_disp;
+  const int P1 = c.p1 * c.bf_width * c.bf_height, P2 = c.p2 * c.bf_width * c.bf_height; // core.cu:670-671
+  const int cmax = census_bits(c.census_width, c.census_height) * c.bf_width * c.bf_height;
+  const bool fast = aggr_fast_supported(D, cmax, P1, P2);
+  if (!fast) { int r = e->ensure_generic_volumes(); if (r) return r; }
+  const size_t fsz = e->fsz(), msz = (size_t)rows * cols;
+  int launches = 0;
+  for (int w0 = 0; w0 < c.batch; w0 += e->wave) {
+    const int wn = std::min(e->wave, c.batch - w0);
+    FrontParams fp{};
+    if (kind == IN_U8) {
+      fp.left_u8 = static_cast<const uint8_t *>(left) + (size_t)w0 * fsz;
+      fp.right_u8 = static_cast<const uint8_t *>(right) + (size_t)w0 * fsz;
+    } else {
+      fp.left_rgba = static_cast<const float *>(left) + (size_t)w0 * fsz * 4;
+      fp.right_rgba = static_cast<const float *>(right) + (size_t)w0 * fsz * 4;
+    }
+    fp.mapLx = e->mapLx; fp.mapLy = e->mapLy; fp.mapRx = e->mapRx; fp.mapRy = e->mapRy;
+    fp.frows = (int)c.rows; fp.fcols = (int)c.cols; fp.bx = bx; fp.by = by;
+    fp.rows = rows; fp.cols = cols; fp.cw = c.census_width; fp.ch = c.census_height; fp.N = wn;
+    fp.im0 = e->im0 + (size_t)w0 * msz; fp.im1 = e->im1 + (size_t)w0 * msz;
+    fp.census0 = e->cen0 + (size_t)w0 * msz; fp.census1 = e->cen1 + (size_t)w0 * msz;
+    fp.speckle_shape = c.speckle_shape; fp.speckle_scale = c.speckle_scale;
+    fp.gaussian_mu = c.gaussian_mu; fp.gaussian_sigma = c.gaussian_sigma;
+    fp.seed = c.ir_noise_seed; fp.frame = e->frame;
+    CK(launch_front(fp, st));
+    e->mark("front");
+    CK(launch_cost(fp.census0, fp.census1, e->C, wn, rows, cols, D, c.bf_width, c.bf_height, st));
+    e->mark("cost");
+    AggrBuffers ab{};
+    ab.C = e->C; ab.L1 = e->L1; ab.L2 = e->L2; ab.S3 = e->S3;
+    ab.dbgL0 = e->dbgL0; ab.dbgL3 = e->dbgL3; ab.dbgLAll = e->dbgLAll;
+    ab.dispL = e->dispL + (size_t)w0 * msz; ab.dispR = e->dispR + (size_t)w0 * msz;
+    if (fast) {
+      if (!c.keep_stages) { ab.dbgL0 = ab.dbgL3 = ab.dbgLAll = nullptr; }
+      CK(launch_aggr_wta(ab, wn, rows, cols, D, P1, P2, c.uniq_ratio, st, e->aux, e->ev));
+      launches += 6;
+    } else {
+      CK(launch_aggr_wta_generic(ab, nullptr, wn, rows, cols, D, P1, P2, c.uniq_ratio, st));
+      launches += 8;
+    }
+    e->mark("aggr_wta");
+  }
+  PostParams pp{};
+  pp.N = c.batch; pp.rows = rows; pp.cols = cols; pp.frows = (int)c.rows; pp.fcols = (int)c.cols;
+  pp.bx = bx; pp.by = by; pp.bbox = use_bbox; pp.lr_max_diff = c.lr_max_diff; pp.mf_size = c.mf_size;
+  pp.focal = c.focal_len; pp.baseline = c.baseline_len; pp.min_depth = c.min_depth; pp.max_depth = c.max_depth;
+  pp.dispL = e->dispL; pp.dispR = e->dispR;
+  pp.disp_lr = c.keep_stages ? e->disp_lr : nullptr;
+  pp.disp_med = e->disp_med;
+  pp.disp_full = use_bbox ? e->disp_full : e->disp_med;
+  pp.depth = e->depth;
+  pp.registration = c.registration; pp.dilation = c.dilation;
+  pp.a1 = e->a1; pp.a2 = e->a2; pp.a3 = e->a3; pp.b1 = c.b1; pp.b2 = c.b2; pp.b3 = c.b3;
+  pp.rgb_rows = (int)c.rgb_rows; pp.rgb_cols = (int)c.rgb_cols;
+  pp.canvas = e->canvas; pp.out = e->out;
+  int pl = 0;
+  CK(launch_post(pp, st, &pl));
+  launches += pl;
+  e->mark("post");
+  e->launches = launches;
+  e->mrows = rows; e->mcols = cols;
+  e->frame++;
+  if (user && user != st) {
+    CK(cudaEventRecord(e->ev_out, st));
+    CK(cudaStreamWaitEvent(user, e->ev_out, 0));
+  }
+  e->computed = true;
+  return SS_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *ss_last_error(void) { return g_err.c_str(); }
+const char *ss_version(void) { return "ss_b200 0.1 (sm_100a)"; }
+
+int ss_create(const ss_config *cfg, const float *mapLx, const float *mapLy, const float *mapRx,
+              const float *mapRy, const float *a1, const float *a2, const float *a3,
+              ss_engine **out) {
+  if (!cfg || !out) return fail(SS_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int r = validate_params(*cfg);
+  if (r) return r;
+  if (cfg->batch < 1) return fail(SS_ERR_INVALID, "batch must be >= 1");
+  if (cfg->registration && (cfg->rgb_rows < 1 || cfg->rgb_cols < 1)) return fail(SS_ERR_INVALID, "RGB resolution must be positive");
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    return fail(SS_ERR_NO_DEVICE, "no CUDA device: the B200 stereo depth engine has no CPU fallback");
+  int dev = cfg->device;
+  if (dev < 0) CK(cudaGetDevice(&dev));
+  if (dev >= count) return fail(SS_ERR_INVALID, "device ordinal out of range");
+  cudaDeviceProp prop{};
+  CK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail(SS_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100: this build targets B200 only");
+  DeviceGuard g(dev);
+  if (!g.ok) return fail(SS_ERR_CUDA, "cudaSetDevice failed");
+  ss_engine *e = new ss_engine();
+  e->cfg = *cfg;
+  if (e->cfg.lr_max_diff == -1) e->cfg.lr_max_diff = 255; // uint8_t wrap in the reference ctor
+  e->device = dev;
+  e->cfg.device = dev;
+  r = create_impl(e, mapLx, mapLy, mapRx, mapRy, a1, a2, a3);
+  if (r) { std::string keep = g_err; ss_destroy(e); g_err = keep; return r; }
+  *out = e;
+  return SS_OK;
+}
+
+int ss_destroy(ss_engine *e) {
+  if (!e) return SS_OK;
+  DeviceGuard g(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->aux) cudaStreamSynchronize(e->aux);
+  for (void *p : e->allocs) cudaFree(p);
+  for (auto ev : e->pev) cudaEventDestroy(ev);
+  for (auto ev : e->ev) if (ev) cudaEventDestroy(ev);
+  if (e->ev_in) cudaEventDestroy(e->ev_in);
+  if (e->ev_out) cudaEventDestroy(e->ev_out);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  if (e->aux) cudaStreamDestroy(e->aux);
+  delete e;
+  return SS_OK;
+}
+
+int ss_compute_host_u8(ss_engine *e, const uint8_t *left, const uint8_t *right, const ss_bbox *bbox) {
+  if (!e || !left || !right) return fail(SS_ERR_INVALID, "null argument");
+  DeviceGuard g(e->device);
+  const size_t bytes = (size_t)e->cfg.batch * e->fsz();
+  CK(cudaMemcpyAsync(e->raw0, left, bytes, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->raw1, right, bytes, cudaMemcpyHostToDevice, e->stream));
+  int r = compute_impl(e, IN_U8, e->raw0, e->raw1, bbox, nullptr);
+  if (r) return r;
+  CK(cudaStreamSynchronize(e->stream));
+  return SS_OK;
+}
+
+int ss_compute_device_rgba_f32(ss_engine *e, const void *left, const void *right, const ss_bbox *bbox, void *stream) {
+  if (!e) return fail(SS_ERR_INVALID, "null engine");
+  DeviceGuard g(e->device);
+  return compute_impl(e, IN_RGBA, left, right, bbox, static_cast<cudaStream_t>(stream));
+}
+
+int ss_compute_device_u8(ss_engine *e, const void *left, const void *right, const ss_bbox *bbox, void *stream) {
+  if (!e) return fail(SS_ERR_INVALID, "null engine");
+  DeviceGuard g(e->device);
+  return compute_impl(e, IN_U8, left, right, bbox, static_cast<cudaStream_t>(stream));
+}
+
+int ss_synchronize(ss_engine *e) {
+  if (!e) return fail(SS_ERR_INVALID, "null engine");
+  DeviceGuard g(e->device);
+  CK(cudaStreamSynchronize(e->stream));
+  return SS_OK;
+}
+
+int ss_get_output_shape(const ss_engine *e, uint32_t *rows, uint32_t *cols) {
+  if (!e || !rows || !cols) return fail(SS_ERR_INVALID, "null argument");
+  *rows = e->out_rows(); *cols = e->out_cols();
+  return SS_OK;
+}
+int ss_get_input_shape(const ss_engine *e, uint32_t *rows, uint32_t *cols) {
+  if (!e || !rows || !cols) return fail(SS_ERR_INVALID, "null argument");
+  *rows = e->cfg.rows; *cols = e->cfg.cols;
+  return SS_OK;
+}
+int ss_get_device(const ss_engine *e, int32_t *device) {
+  if (!e || !device) return fail(SS_ERR_INVALID, "null argument");
+  *device = e->device;
+  return SS_OK;
+}
+
+static int copy_out(ss_engine *e, const float *src, size_t count, float *out, size_t cap) {
+  if (!out) return fail(SS_ERR_INVALID, "null output");
+  if (cap < count * sizeof(float)) return fail(SS_ERR_INVALID, "output buffer too small");
+  CK(cudaMemcpyAsync(out, src, count * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return SS_OK;
+}
+
+int ss_get_depth_host(ss_engine *e, float *out, size_t cap) {
+  if (!e) return fail(SS_ERR_INVALID, "null engine");
+  if (!e->computed) return fail(SS_ERR_NOT_COMPUTED, "No computed data stored");
+  DeviceGuard g(e->device);
+  return copy_out(e, e->out, (size_t)e->cfg.batch * e->rsz(), out, cap);
+}
+int ss_get_depth_device(ss_engine *e, void **ptr) {
+  if (!e || !ptr) return fail(SS_ERR_INVALID, "null argument");
+  if (!e->computed) return fail(SS_ERR_NOT_COMPUTED, "No computed data stored");
+  *ptr = e->out;
+  return SS_OK;
+}
+static int run_pc(ss_engine *e, const void *rgba) {
+  const ss_config &c = e->cfg;
+  CK(launch_point_cloud(e->out, static_cast<const float *>(rgba), rgba ? e->rgbpc : e->pc, c.batch,
+                        (int)e->out_rows(), (int)e->out_cols(), c.main_fx, c.main_fy, c.main_skew,
+                        c.main_cx, c.main_cy, e->stream));
+  return SS_OK;
+}
+int ss_get_point_cloud_host(ss_engine *e, float *out, size_t cap) {
+  if (!e) return fail(SS_ERR_INVALID, "null engine");
+  if (!e->computed) return fail(SS_ERR_NOT_COMPUTED, "No computed data stored");
+  DeviceGuard g(e->device);
+  int r = run_pc(e, nullptr);
+  if (r) return r;
+  return copy_out(e, e->pc, (size_t)e->cfg.batch * e->rsz() * 3, out, cap);
+}
+int ss_get_point_cloud_device(ss_engine *e, void **ptr) {
+  if (!e || !ptr) return fail(SS_ERR_INVALID, "null argument");
+  if (!e->computed) return fail(SS_ERR_NOT_COMPUTED, "No computed data stored");
+  DeviceGuard g(e->device);
+  int r = run_pc(e, nullptr);
+  if (r) return r;
+  CK(cudaStreamSynchronize(e->stream)); // the reference's getter is synchronous (core.cu:409-411)
+  *ptr = e->pc;
+  return SS_OK;
+}
+int ss_get_rgb_point_cloud_host(ss_engine *e, const void *rgba, float *out, size_t cap) {
+  if (!e || !rgba) return fail(SS_ERR_INVALID, "null argument");
+  if (!e->computed) return fail(SS_ERR_NOT_COMPUTED, "No computed data stored");
+  DeviceGuard g(e->device);
+  int r = run_pc(e, rgba);
+  if (r) return r;
+  return copy_out(e, e->rgbpc, (size_t)e->cfg.batch * e->rsz() * 6, out, cap);
+}
+int ss_get_rgb_point_cloud_device(ss_engine *e, const void *rgba, void **ptr) {
+  if (!e || !rgba || !ptr) return fail(SS_ERR_INVALID, "null argument");
+  if (!e->computed) return fail(SS_ERR_NOT_COMPUTED, "No computed data stored");
+  DeviceGuard g(e->device);
+  int r = run_pc(e, rgba);
+  if (r) return r;
+  CK(cudaStreamSynchronize(e->stream));
+  *ptr = e->rgbpc;
+  return SS_OK;
+}
+
+int ss_set_ir_noise_parameters(ss_engine *e, float shape, float scale, float mu, float sigma) {
+  if (!e) return fail(SS_ERR_INVALID, "null engine");
+  e->cfg.speckle_shape = shape; e->cfg.speckle_scale = scale;
+  e->cfg.gaussian_mu = mu; e->cfg.gaussian_sigma = sigma;
+  return SS_OK;
+}
+#define SET_VALIDATED(body)                                                                       \
+  if (!e) return fail(SS_ERR_INVALID, "null engine");                                             \
+  ss_config t = e->cfg;                                                                           \
+  body;                                                                                           \
+  int r = validate_params(t);                                                                     \
+  if (r) return r;                                                                                \
+  e->cfg = t;                                                                                     \
+  return SS_OK;
+int ss_set_penalties(ss_engine *e, int32_t p1, int32_t p2) { SET_VALIDATED(t.p1 = p1; t.p2 = p2) }
+int ss_set_census_window_size(ss_engine *e, int32_t w, int32_t h) { SET_VALIDATED(t.census_width = w; t.census_height = h) }
+int ss_set_matching_block_size(ss_engine *e, int32_t w, int32_t h) { SET_VALIDATED(t.bf_width = w; t.bf_height = h) }
+int ss_set_uniqueness_ratio(ss_engine *e, int32_t u) { SET_VALIDATED(t.uniq_ratio = u) }
+int ss_set_lr_max_diff(ss_engine *e, int32_t d) { SET_VALIDATED(t.lr_max_diff = (d == -1 ? 255 : d)) }
+
+int ss_get_stage_host(ss_engine *e, const char *name, int32_t index, void *out, size_t cap, size_t *bytes) {
+  if (!e || !name || !out) return fail(SS_ERR_INVALID, "null argument");
+  if (!e->computed) return fail(SS_ERR_NOT_COMPUTED, "No computed data stored");
+  if (index < 0 || index >= e->cfg.batch) return fail(SS_ERR_INVALID, "batch index out of range");
+  DeviceGuard g(e->device);
+  const std::string n(name);
+  const size_t msz = (size_t)e->mrows * e->mcols, fsz = e->fsz(), D = (size_t)e->cfg.max_disp;
+  const void *src = nullptr;
+  size_t sz = 0;
+  auto pix = [&](const void *base, size_t elem, size_t per) { src = static_cast<const char *>(base) + (size_t)index * per * elem; sz = per * elem; };
+  auto vol = [&](const uint16_t *base) -> int {
+    if (!base) return fail(SS_ERR_INVALID, "stage '" + n + "' needs keep_stages=1");
+    if (e->cfg.batch > e->wave) return fail(SS_ERR_INVALID, "volume stages are only kept when the batch fits one wave");
+    src = base + (size_t)index * msz * D; sz = msz * D * 2;
+    return SS_OK;
+  };
+  int r = SS_OK;
+  if (n == "im0") pix(e->im0, 1, msz);
+  else if (n == "im1") pix(e->im1, 1, msz);
+  else if (n == "census0") pix(e->cen0, 4, msz);
+  else if (n == "census1") pix(e->cen1, 4, msz);
+  else if (n == "cost") r = vol(e->C);
+  else if (n == "L1") r = vol(e->L1);
+  else if (n == "L2") r = vol(e->cfg.keep_stages ? e->L2 : nullptr);
+  else if (n == "L0") r = vol(e->cfg.keep_stages ? e->dbgL0 : nullptr);
+  else if (n == "L3") r = vol(e->cfg.keep_stages ? e->dbgL3 : nullptr);
+  else if (n == "LAll") r = vol(e->cfg.keep_stages ? e->dbgLAll : nullptr);
+  else if (n == "disp_wta") pix(e->dispL, 4, msz);
+  else if (n == "disp_right") pix(e->dispR, 2, msz);
+  else if (n == "disp_lr") { if (!e->cfg.keep_stages) return fail(SS_ERR_INVALID, "stage 'disp_lr' needs keep_stages=1"); pix(e->disp_lr, 4, msz); }
+  else if (n == "disp_med") pix(e->disp_med, 4, msz);
+  else if (n == "disp_full") pix(e->mrows == (int)e->cfg.rows && e->mcols == (int)e->cfg.cols ? e->disp_med : e->disp_full, 4, fsz);
+  else if (n == "depth") pix(e->depth, 4, fsz);
+  else return fail(SS_ERR_INVALID, "unknown stage '" + n + "'");
+  if (r) return r;
+  if (bytes) *bytes = sz;
+  if (cap < sz) return fail(SS_ERR_INVALID, "output buffer too small");
+  CK(cudaMemcpyAsync(out, src, sz, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return SS_OK;
+}
+
+int ss_pointer_device(const void *ptr, int32_t *device) {
+  if (!device) return fail(SS_ERR_INVALID, "null argument");
+  cudaPointerAttributes attr{};
+  cudaError_t err = cudaPointerGetAttributes(&attr, ptr);
+  if (err != cudaSuccess) { cudaGetLastError(); *device = -1; return fail(SS_ERR_CUDA, cudaGetErrorString(err)); }
+  *device = (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) ? attr.device : -1;
+  return SS_OK;
+}
+
+int ss_set_profiling(ss_engine *e, int32_t enabled) {
+  if (!e) return fail(SS_ERR_INVALID, "null engine");
+  e->profiling = enabled != 0;
+  return SS_OK;
+}
+int ss_get_stage_times(ss_engine *e, const char **names, float *ms, int32_t capacity, int32_t *count) {
+  if (!e || !count) return fail(SS_ERR_INVALID, "null argument");
+  DeviceGuard g(e->device);
+  CK(cudaStreamSynchronize(e->stream));
+  const int n = (int)e->pev.size() - 1;
+  *count = std::max(n, 0);
+  for (int i = 0; i < n && i < capacity; ++i) {
+    float t = 0;
+    CK(cudaEventElapsedTime(&t, e->pev[i], e->pev[i + 1]));
+    if (names) names[i] = e->pnames[i + 1];
+    if (ms) ms[i] = t;
+  }
+  return SS_OK;
+}
+int ss_get_launches_per_compute(ss_engine *e, int32_t *count) {
+  if (!e || !count) return fail(SS_ERR_INVALID, "null argument");
+  *count = e->launches;
+  return SS_OK;
+}
+
+} // extern "C"

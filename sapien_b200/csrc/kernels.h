@@ -1,0 +1,85 @@
+// kernels.h -- host-callable launchers of the sm_100a kernels (one .cu per stage group).
+// All launchers enqueue on `stream` and return the cudaError_t of the launch.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace ssb {
+
+// ---------------------------------------------------------------------------- front.cu
+struct FrontParams {
+  // sources: exactly one of src_u8 / src_rgba per image is non-null.  [N][frows][fcols](x4)
+  const uint8_t *left_u8, *right_u8;
+  const float *left_rgba, *right_rgba;
+  const float *mapLx, *mapLy, *mapRx, *mapRy; // null when rectified
+  int frows, fcols;                           // full IR size
+  int bx, by;                                 // ROI origin (0,0 when no bbox)
+  int rows, cols;                             // matched (ROI) size
+  int cw, ch;                                 // census window
+  int N;
+  uint8_t *im0, *im1;                         // [N][rows][cols] prepared images (census input)
+  uint32_t *census0, *census1;                // [N][rows][cols]
+  // optional IR noise (speckle_shape > 0): applied to the source texel before remap
+  float speckle_shape, speckle_scale, gaussian_mu, gaussian_sigma;
+  uint64_t seed;
+  uint64_t frame; // frame counter (decorrelates successive frames)
+};
+cudaError_t launch_front(const FrontParams &p, cudaStream_t stream);
+
+// ----------------------------------------------------------------------------- cost.cu
+// C[n][y][x][d] = sum over the bw x bh replicate-border block of popc(cL(y,x) ^ cR(y,max(x-d,0)))
+cudaError_t launch_cost(const uint32_t *cL, const uint32_t *cR, uint16_t *C, int N, int rows,
+                        int cols, int D, int bw, int bh, cudaStream_t stream);
+
+// ----------------------------------------------------------------------------- aggr.cu
+// true when the packed-u16 DPX path is valid for this configuration
+bool aggr_fast_supported(int D, int cmax, int P1, int P2);
+struct AggrBuffers {
+  const uint16_t *C; // cost volume
+  uint16_t *L1;      // right->left path
+  uint16_t *L2;      // top->bottom path
+  uint16_t *S3;      // L1+L2+L3 (may alias L2)
+  uint16_t *dbgL0, *dbgL3, *dbgLAll; // optional (keep_stages), else null
+  float *dispL;      // [N][rows][cols] WTA left disparity (uniqueness + sub-pixel), -1 invalid
+  uint16_t *dispR;   // [N][rows][cols] WTA right disparity
+};
+// Runs the 4 path aggregations + blend + winner-takes-all.  s_aux is a second stream used to
+// overlap the two independent first passes; ev[0..1] are scratch events.
+cudaError_t launch_aggr_wta(const AggrBuffers &b, int N, int rows, int cols, int D, int P1, int P2,
+                            int uniq, cudaStream_t stream, cudaStream_t s_aux, cudaEvent_t *ev);
+// Generic (any D, 32-bit math) fallback with the same contract; needs scratch volumes.
+cudaError_t launch_aggr_wta_generic(const AggrBuffers &b, uint16_t *L0scratch, int N, int rows,
+                                    int cols, int D, int P1, int P2, int uniq,
+                                    cudaStream_t stream);
+
+// ----------------------------------------------------------------------------- post.cu
+struct PostParams {
+  int N;
+  int rows, cols;   // matched size
+  int frows, fcols; // full IR size
+  int bx, by;
+  int bbox;         // 1: ROI paste into a zeroed full-size map
+  int lr_max_diff, mf_size;
+  float focal, baseline, min_depth, max_depth;
+  const float *dispL;      // [N][rows][cols] from WTA
+  const uint16_t *dispR;   // [N][rows][cols]
+  float *disp_lr;          // optional stage out [N][rows][cols]
+  float *disp_med;         // [N][rows][cols]
+  float *disp_full;        // [N][frows][fcols] (== disp_med layout when !bbox; may alias)
+  float *depth;            // [N][frows][fcols]
+  // registration
+  int registration, dilation;
+  const float *a1, *a2, *a3; // [frows][fcols]
+  float b1, b2, b3;
+  int rgb_rows, rgb_cols;
+  float *canvas;   // [N][rgb_rows][rgb_cols] splat target
+  float *out;      // final depth: [N][rgb_rows][rgb_cols] or [N][frows][fcols]
+};
+cudaError_t launch_post(const PostParams &p, cudaStream_t stream, int *launches);
+
+cudaError_t launch_point_cloud(const float *depth, const float *rgba, float *pc, int N, int rows,
+                               int cols, float fx, float fy, float skew, float cx, float cy,
+                               cudaStream_t stream);
+
+} // namespace ssb

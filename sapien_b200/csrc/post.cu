@@ -1,0 +1,197 @@
+// post.cu -- disparity post-processing and depth output for sm_100a.
+//
+// Replaces lrConsistencyCheck (3rd_party/simsense/src/lrcheck.cu:21-32), medianFilter
+// (src/filter.cu:98-117), pasteSubArea (src/camera.cu:141-158), disp2Depth (:160-168),
+// initRgbDepth / depthRegistration / depthDilation / correctDepthRange (:170-240) and the two
+// point-cloud kernels (:242-286).  The reference runs these as 8 launches with device-wide
+// syncs; here: LR check + median + ROI paste in one tile kernel (median by a register sorting
+// network instead of a per-thread selection sort in shared memory), disparity->depth +
+// registration splat in one, dilation + range clamp in one.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ssb {
+
+// ------------------------------------------------------------------ LR check + median + paste
+template <int N> __device__ __forceinline__ void bitonic_sort(float (&a)[N]) {
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const int l = i ^ j;
+        if (l > i) {
+          const float lo = fminf(a[i], a[l]), hi = fmaxf(a[i], a[l]);
+          if ((i & k) == 0) { a[i] = lo; a[l] = hi; }
+          else { a[i] = hi; a[l] = lo; }
+        }
+      }
+    }
+  }
+}
+
+constexpr int PT_X = 32, PT_Y = 8;
+
+template <int K>
+__global__ void __launch_bounds__(PT_X *PT_Y) lr_median_kernel(const PostParams p) {
+  constexpr int H = K / 2;
+  constexpr int WC = PT_X + 2 * H, WR = PT_Y + 2 * H;
+  __shared__ float tile[WR][WC];
+  const int n = blockIdx.z;
+  const int x0 = blockIdx.x * PT_X, y0 = blockIdx.y * PT_Y;
+  const size_t img = (size_t)n * p.rows * p.cols;
+  const int tid = threadIdx.y * PT_X + threadIdx.x;
+  for (int i = tid; i < WR * WC; i += PT_X * PT_Y) {
+    const int wy = i / WC, wx = i - wy * WC;
+    const int y = y0 + wy - H, x = x0 + wx - H;
+    float v = -1.0f;
+    if (x >= 0 && x < p.cols && y >= 0 && y < p.rows) {
+      const size_t pos = img + (size_t)y * p.cols + x;
+      v = p.dispL[pos];
+      if (p.lr_max_diff != 255) { // lrcheck.cu:28-31
+        const int ld = (int)roundf(v);
+        if (ld < 0 || x - ld < 0 || abs(ld - (int)p.dispR[pos - ld]) > p.lr_max_diff) v = -1.0f;
+      }
+      if (p.disp_lr && wy >= H && wy < WR - H && wx >= H && wx < WC - H) p.disp_lr[pos] = v;
+    }
+    tile[wy][wx] = v;
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  if (x >= p.cols || y >= p.rows) return;
+  float out = tile[threadIdx.y + H][threadIdx.x + H];
+  if (K > 1 && x >= H && y >= H && x < p.cols - H && y < p.rows - H) { // filter.cu:107
+    constexpr int NN = K * K;
+    constexpr int NP = NN <= 16 ? 16 : (NN <= 32 ? 32 : 64);
+    float a[NP];
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+      for (int i = 0; i < K; ++i) a[j * K + i] = tile[threadIdx.y + j][threadIdx.x + i];
+#pragma unroll
+    for (int i = NN; i < NP; ++i) a[i] = __int_as_float(0x7f800000);
+    bitonic_sort<NP>(a);
+    out = a[NN / 2];
+  }
+  p.disp_med[img + (size_t)y * p.cols + x] = out;
+  if (p.bbox)
+    p.disp_full[((size_t)n * p.frows + (y + p.by)) * p.fcols + x + p.bx] = out;
+}
+
+// ------------------------------------------------------------------ depth + registration splat
+__device__ __forceinline__ float atomic_min_float(float *addr, float value) { // camera.cu:42-47
+  return (value >= 0) ? __int_as_float(atomicMin((int *)addr, __float_as_int(value)))
+                      : __uint_as_float(atomicMax((unsigned int *)addr, __float_as_uint(value)));
+}
+
+__global__ void fill_kernel(float *dst, size_t n, float v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = v;
+}
+
+__global__ void __launch_bounds__(256) depth_splat_kernel(const PostParams p) {
+  const size_t fsz = (size_t)p.frows * p.fcols;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= fsz * p.N) return;
+  const size_t n = idx / fsz;
+  const size_t pos = idx - n * fsz;
+  const float d = p.disp_full[idx];
+  const float z = (d <= 0) ? 0 : p.focal * p.baseline / d; // camera.cu:167
+  p.depth[idx] = z;
+  if (p.registration) { // camera.cu:187-195, same expression shapes so nvcc contracts identically
+    const float zRgb = p.a3[pos] * z + p.b3;
+    const int x = (int)roundf((p.a1[pos] * z + p.b1) / zRgb);
+    const int y = (int)roundf((p.a2[pos] * z + p.b2) / zRgb);
+    if (zRgb > 0 && x >= 0 && x < p.rgb_cols && y >= 0 && y < p.rgb_rows)
+      atomic_min_float(p.canvas + (n * p.rgb_rows + y) * p.rgb_cols + x, zRgb);
+  } else {
+    p.out[idx] = (z < p.min_depth || z >= p.max_depth) ? 0.0f : z; // camera.cu:237-239
+  }
+}
+
+// Dilation with snapshot semantics + range clamp, canvas -> out.
+__global__ void __launch_bounds__(256) dilate_range_kernel(const PostParams p) {
+  const size_t rsz = (size_t)p.rgb_rows * p.rgb_cols;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rsz * p.N) return;
+  const size_t pos = idx % rsz;
+  const int y = (int)(pos / p.rgb_cols), x = (int)(pos - (size_t)y * p.rgb_cols);
+  float m = p.canvas[idx];
+  if (p.dilation) { // camera.cu:207-227: a pixel < maxDepth lowers its left, top, top-left
+    const bool xr = x + 1 < p.rgb_cols, yb = y + 1 < p.rgb_rows;
+    float t;
+    if (xr && (t = p.canvas[idx + 1]) < p.max_depth) m = fminf(m, t);
+    if (yb && (t = p.canvas[idx + p.rgb_cols]) < p.max_depth) m = fminf(m, t);
+    if (xr && yb && (t = p.canvas[idx + p.rgb_cols + 1]) < p.max_depth) m = fminf(m, t);
+  }
+  p.out[idx] = (m < p.min_depth || m >= p.max_depth) ? 0.0f : m;
+}
+
+cudaError_t launch_post(const PostParams &p, cudaStream_t st, int *launches) {
+  if (p.N > 65535) return cudaErrorInvalidValue;
+  int nl = 0;
+  cudaError_t err;
+  const size_t fsz = (size_t)p.frows * p.fcols * p.N;
+  const size_t rsz = (size_t)p.rgb_rows * p.rgb_cols * p.N;
+  if (p.bbox) { // outside-ROI disparity is defined as 0 (reference leaves it uninitialised)
+    if ((err = cudaMemsetAsync(p.disp_full, 0, fsz * sizeof(float), st)) != cudaSuccess) return err;
+  }
+  if (p.registration) {
+    fill_kernel<<<(unsigned)min((rsz + 255) / 256, (size_t)148 * 16), 256, 0, st>>>(p.canvas, rsz, p.max_depth);
+    ++nl;
+  }
+  const dim3 grid((p.cols + PT_X - 1) / PT_X, (p.rows + PT_Y - 1) / PT_Y, p.N);
+  const dim3 block(PT_X, PT_Y);
+  switch (p.mf_size) {
+  case 1: lr_median_kernel<1><<<grid, block, 0, st>>>(p); break;
+  case 3: lr_median_kernel<3><<<grid, block, 0, st>>>(p); break;
+  case 5: lr_median_kernel<5><<<grid, block, 0, st>>>(p); break;
+  case 7: lr_median_kernel<7><<<grid, block, 0, st>>>(p); break;
+  default: return cudaErrorInvalidValue;
+  }
+  ++nl;
+  depth_splat_kernel<<<(unsigned)((fsz + 255) / 256), 256, 0, st>>>(p);
+  ++nl;
+  if (p.registration) {
+    dilate_range_kernel<<<(unsigned)((rsz + 255) / 256), 256, 0, st>>>(p);
+    ++nl;
+  }
+  if (launches) *launches = nl;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------ point clouds
+template <bool RGB>
+__global__ void __launch_bounds__(256)
+point_cloud_kernel(const float *__restrict__ depth, const float *__restrict__ rgba,
+                   float *__restrict__ pc, size_t total, int rows, int cols, float fx, float fy,
+                   float s, float cx, float cy) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const size_t pos = idx % ((size_t)rows * cols);
+  const int u = (int)(pos % cols), v = (int)(pos / cols);
+  const float z = depth[idx]; // camera.cu:250-260
+  const float x = z * ((u - cx) / fx + s * (cy - v) / (fx * fy));
+  const float y = z * (v - cy) / fy;
+  if (RGB) {
+    const float4 c = __ldg(reinterpret_cast<const float4 *>(rgba) + idx);
+    float2 *o = reinterpret_cast<float2 *>(pc + 6 * idx);
+    o[0] = make_float2(x, y); o[1] = make_float2(z, c.x); o[2] = make_float2(c.y, c.z);
+  } else {
+    pc[3 * idx] = x; pc[3 * idx + 1] = y; pc[3 * idx + 2] = z;
+  }
+}
+
+cudaError_t launch_point_cloud(const float *depth, const float *rgba, float *pc, int N, int rows,
+                               int cols, float fx, float fy, float skew, float cx, float cy,
+                               cudaStream_t st) {
+  const size_t total = (size_t)N * rows * cols;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (rgba) point_cloud_kernel<true><<<blocks, 256, 0, st>>>(depth, rgba, pc, total, rows, cols, fx, fy, skew, cx, cy);
+  else point_cloud_kernel<false><<<blocks, 256, 0, st>>>(depth, nullptr, pc, total, rows, cols, fx, fy, skew, cx, cy);
+  return cudaGetLastError();
+}
+
+} // namespace ssb

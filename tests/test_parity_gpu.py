@@ -1,0 +1,361 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA engine, driven through the pybind layer
+over the C ABI, against (a) the scalar C oracle and (b) the unmodified reference simsense CUDA code
+(oracle/_ref).  Integer stages must match bit-for-bit; float outputs within the north_star
+tolerances (<=1e-3 px sub-pixel disparity, <=1e-4 relative depth) -- in practice disparity and the
+IR-frame depth are bit-exact too."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import REF_SO, RefEngine, configs
+from sapien_b200 import synth
+from tests.common import (assert_depth_close, assert_stages_equal, get_stage, make_engine, variant)
+
+pytestmark = pytest.mark.gpu
+
+SMALL_VARIANTS = {
+    "default": {},
+    "rectified": dict(rectified=True),
+    "no_lr": dict(lr_max_diff=255),
+    "lr0": dict(lr_max_diff=0),
+    "lr3": dict(lr_max_diff=3),
+    "mf1": dict(mf_size=1),
+    "mf5": dict(mf_size=5),
+    "mf7": dict(mf_size=7),
+    "bf1": dict(bf_width=1, bf_height=1),
+    "bf3": dict(bf_width=3, bf_height=3),
+    "bf5": dict(bf_width=5, bf_height=5),
+    "bf9": dict(bf_width=9, bf_height=9),
+    "bf3x5_generic_cost": dict(bf_width=3, bf_height=5),
+    "bf11x1_generic_cost": dict(bf_width=11, bf_height=1),
+    "census5": dict(census_width=5, census_height=5),
+    "census9x7": dict(census_width=9, census_height=7),
+    "census3": dict(census_width=3, census_height=3),
+    "census13x5": dict(census_width=13, census_height=5),
+    "uniq0": dict(uniq_ratio=0),
+    "uniq50": dict(uniq_ratio=50),
+    "uniq100": dict(uniq_ratio=100),
+    "uniq180": dict(uniq_ratio=180),
+    "p_small": dict(p1=1, p2=2),
+    "p_large": dict(p1=100, p2=223),
+    "no_dilation": dict(dilation=False),
+    "d48": dict(max_disp=48),
+    "d64": dict(max_disp=64),
+    "d96": dict(max_disp=96),
+    "d100": dict(max_disp=100),
+    "d128_wider_than_image": dict(max_disp=128),
+    "d160": dict(max_disp=160),
+    "d256": dict(max_disp=256),
+    "d33_generic_aggr": dict(max_disp=33),
+    "d130_generic_aggr": dict(max_disp=130),
+    "wide_regime_generic_aggr": dict(bf_width=15, bf_height=15, p1=100, p2=223),
+    "depth_range": dict(min_depth=0.5, max_depth=1.0),
+}
+
+
+def run_ours(native, prm, left, right, bbox=None, **kw):
+    eng = make_engine(native, prm, **kw)
+    if bbox is None:
+        eng.compute(left, right)
+    else:
+        eng.compute(left, right, True, *bbox)
+    return eng
+
+
+@pytest.mark.parametrize("name", list(SMALL_VARIANTS))
+def test_small_all_stages_vs_oracle(native, oracle, name):
+    prm = variant(configs.params("small"), **SMALL_VARIANTS[name])
+    left, right = configs.pair(prm, seed=3)
+    ref = oracle.pipeline(prm, left, right)
+    eng = run_ours(native, prm, left, right, keep_stages=True)
+    assert_stages_equal(eng, prm, ref)
+    assert_depth_close(eng.get_ndarray(), ref["out"])
+    # the production configuration (no stage materialisation) gives the same final results
+    fast = run_ours(native, prm, left, right)
+    assert_stages_equal(fast, prm, ref, names=("census0", "census1", "cost", "disp_wta", "disp_right", "disp_med", "depth"))
+    assert np.array_equal(fast.get_ndarray().view(np.uint32), eng.get_ndarray().view(np.uint32))
+
+
+@pytest.mark.parametrize("cfg", ["small435", "C4"])
+def test_other_cameras_vs_oracle(native, oracle, cfg):
+    prm = configs.params(cfg)
+    left, right = configs.pair(prm, seed=11)
+    ref = oracle.pipeline(prm, left, right)
+    eng = run_ours(native, prm, left, right, keep_stages=True)
+    assert_stages_equal(eng, prm, ref)
+    assert_depth_close(eng.get_ndarray(), ref["out"])
+
+
+@pytest.mark.parametrize("bbox", [(8, 4, 64, 40), (0, 0, 96, 64), (31, 23, 33, 37), (60, 30, 36, 34)])
+def test_small_bbox_vs_oracle(native, oracle, bbox):
+    prm = configs.params("small")
+    left, right = configs.pair(prm, seed=5)
+    ref = oracle.pipeline(prm, left, right, bbox=bbox)
+    eng = run_ours(native, prm, left, right, bbox=bbox, keep_stages=True)
+    assert_stages_equal(eng, prm, ref, bbox=bbox)
+    assert_depth_close(eng.get_ndarray(), ref["out"])
+
+
+needs_ref = pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/libsimsense_ref.so not built")
+
+REF_STAGE_MAP = [("census0", "census0"), ("census1", "census1"), ("cost", "cost"), ("L0", "L0"), ("L1", "L1"),
+                 ("L2", "L2"), ("LAll", "LAll"), ("disp_right", "rightDisp"), ("depth", "depth")]
+
+
+def compare_with_reference(native, prm, left, right, bbox=None, oracle=None):
+    ref = RefEngine(prm)
+    ref.compute_host(left, right, bbox)
+    eng = run_ours(native, prm, left, right, bbox=bbox, keep_stages=True)
+    bad = []
+    for ours, theirs in REF_STAGE_MAP:
+        a = get_stage(eng, prm, ours, bbox)
+        b = ref.stage(theirs)
+        if not np.array_equal(a.view(np.uint32) if a.dtype.kind == "f" else a, b.view(np.uint32) if b.dtype.kind == "f" else b):
+            bad.append(f"{ours}: {int((a != b).sum())} of {a.size} differ")
+    # left disparity: the reference LR-checks in place, so leftDisp is post-LR
+    a = get_stage(eng, prm, "disp_lr", bbox)
+    b = ref.stage("leftDisp")
+    if not np.array_equal(a.view(np.uint32), b.view(np.uint32)):
+        bad.append(f"disp_lr: {int((a != b).sum())} differ, max abs {np.abs(a - b).max()}")
+    if prm.mf_size != 1:
+        a = get_stage(eng, prm, "disp_med", bbox)
+        b = ref.stage("filteredDisp")
+        if not np.array_equal(a.view(np.uint32), b.view(np.uint32)):
+            bad.append(f"disp_med: {int((a != b).sum())} differ")
+    assert not bad, "\n".join(bad)
+    ours_depth, ref_depth = eng.get_ndarray(), ref.depth()
+    # registration/dilation: float tolerance; the reference dilates in place with atomics
+    #  so report -- and bound -- the number of pixels that differ in validity
+    mism = int(((ours_depth == 0) != (ref_depth == 0)).sum())
+    assert mism == 0, f"{mism} pixels differ in validity from the reference run"
+    assert_depth_close(ours_depth, ref_depth)
+    ref.close()
+    return eng
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["default", "rectified", "no_lr", "mf1", "mf5", "bf1", "bf3", "census5", "uniq50",
+                                  "no_dilation", "d64", "d96", "d128_wider_than_image", "d256", "p_large"])
+def test_small_vs_reference_cuda(native, name):
+    prm = variant(configs.params("small"), **SMALL_VARIANTS[name])
+    left, right = configs.pair(prm, seed=3)
+    compare_with_reference(native, prm, left, right)
+
+
+@needs_ref
+def test_small_bbox_vs_reference_cuda(native):
+    prm = configs.params("small")
+    left, right = configs.pair(prm, seed=5)
+    compare_with_reference(native, prm, left, right, bbox=(8, 4, 64, 40))
+
+
+@needs_ref
+def test_c1_full_size_vs_reference_and_oracle(native, oracle):
+    """BASELINE configs[0]: single D415-like pair 1280x720, 128 disparities, 4-path SGM + LR +
+    median + registration to 1920x1080 -- scalar oracle vs reference simsense vs this engine."""
+    prm = configs.params("C1")
+    left, right = configs.pair(prm, seed=0)
+    eng = compare_with_reference(native, prm, left, right)
+    ref = oracle.pipeline(prm, left, right, volumes=False)
+    assert_stages_equal(eng, prm, ref, names=("im0", "im1", "census0", "census1", "disp_wta", "disp_right", "disp_lr", "disp_med", "depth"))
+    assert_depth_close(eng.get_ndarray(), ref["out"])
+
+
+@needs_ref
+def test_c2_bbox_rgb_point_cloud(native, oracle):
+    """BASELINE configs[1]: same pipeline with bbox ROI compute and RGB point-cloud output."""
+    import torch
+
+    prm = configs.params("C2")
+    left, right = configs.pair(prm, seed=0)
+    eng = compare_with_reference(native, prm, left, right, bbox=configs.BBOX_C2)
+    rgba = synth.make_rgb(prm.rgb_rows, prm.rgb_cols, 0)
+    rgba_t = torch.from_numpy(rgba).cuda()
+    pc = eng.get_rgb_point_cloud_ndarray(rgba_t)
+    want = oracle.pointcloud(eng.get_ndarray(), rgba, prm.main_fx, prm.main_fy, prm.main_skew, prm.main_cx, prm.main_cy)
+    assert pc.shape == (prm.rgb_rows * prm.rgb_cols, 6)
+    np.testing.assert_allclose(pc, want, rtol=1e-4, atol=1e-6)
+    ref = RefEngine(prm)
+    ref.compute_host(left, right, configs.BBOX_C2)
+    np.testing.assert_allclose(pc, ref.rgb_point_cloud(rgba_t.data_ptr()), rtol=1e-4, atol=1e-6)
+    ref.close()
+
+
+def test_c3_batched_envs_vs_oracle(native, oracle):
+    """BASELINE configs[2] shape (848x480, D=96) with a small batch: each env of one batched call
+    equals the oracle run on that env alone."""
+    prm = configs.params("C3")
+    n = 3
+    pairs = [configs.pair(prm, seed=s) for s in range(n)]
+    eng = make_engine(native, prm, batch=n)
+    eng.compute(np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs]))
+    out = eng.get_ndarray()
+    assert out.shape == (n, prm.rgb_rows, prm.rgb_cols)
+    for i, (l, r) in enumerate(pairs):
+        ref = oracle.pipeline(prm, l, r, volumes=False)
+        assert_stages_equal(eng, prm, ref, names=("census0", "disp_wta", "disp_right", "disp_med", "depth"), index=i)
+        assert_depth_close(out[i], ref["out"], what=f"env {i}")
+
+
+def test_c4_many_small_envs_batch_equals_single(native, oracle):
+    """BASELINE configs[3] shape (256x256, D=64): a 16-env batch equals 16 single-env computes."""
+    prm = configs.params("C4")
+    n = 16
+    pairs = [configs.pair(prm, seed=100 + s) for s in range(n)]
+    eng = make_engine(native, prm, batch=n)
+    eng.compute(np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs]))
+    out = eng.get_ndarray()
+    single = make_engine(native, prm)
+    for i, (l, r) in enumerate(pairs):
+        single.compute(l, r)
+        assert np.array_equal(single.get_ndarray().view(np.uint32), out[i].view(np.uint32)), f"env {i}"
+    ref = oracle.pipeline(prm, *pairs[5], volumes=False)
+    assert_depth_close(out[5], ref["out"])
+
+
+def test_c5_highres_d256_properties(native, oracle):
+    """BASELINE configs[4] shape (1920x1080, D=256) at full size: parity with the oracle on the
+    final maps plus size-independent properties (idempotence, disparity bounds)."""
+    prm = configs.params("C5")
+    left, right = configs.pair(prm, seed=0)
+    eng = run_ours(native, prm, left, right)
+    d = get_stage(eng, prm, "disp_med")
+    assert d.max() < prm.max_disp and d.min() >= -1
+    first = eng.get_ndarray().copy()
+    eng.compute(left, right)
+    assert np.array_equal(first.view(np.uint32), eng.get_ndarray().view(np.uint32))
+    ref = oracle.pipeline(prm, left, right, volumes=False)
+    assert_stages_equal(eng, prm, ref, names=("census0", "census1", "disp_wta", "disp_right", "disp_med", "depth"))
+    assert_depth_close(first, ref["out"])
+
+
+def test_device_rgba_input_equals_host_u8(native, oracle):
+    import torch
+
+    prm = configs.params("small")
+    left, right = configs.pair(prm, seed=7)
+    rl, rr = synth.to_rgba(left), synth.to_rgba(right)
+    assert np.array_equal(oracle.float2uint8(rl), left)  # the synthetic RGBA encodes the u8 image exactly
+    tl, tr = torch.from_numpy(rl).cuda(), torch.from_numpy(rr).cuda()
+    eng = make_engine(native, prm)
+    eng.compute(tl, tr)
+    a = eng.get_ndarray().copy()
+    eng.compute(left, right)
+    assert np.array_equal(a.view(np.uint32), eng.get_ndarray().view(np.uint32))
+    # out-of-range / negative floats clamp like core.cu:51-58
+    weird = rl.copy()
+    weird[..., 0].flat[::7] = 1.7
+    weird[..., 0].flat[3::11] = -0.3
+    rect = make_engine(native, variant(prm, rectified=True))
+    rect.compute(torch.from_numpy(weird).cuda(), tr)
+    assert np.array_equal(get_stage(rect, prm, "im0"), oracle.float2uint8(weird))
+    # device uint8 input (extension)
+    eng.compute(torch.from_numpy(left).cuda(), torch.from_numpy(right).cuda())
+    assert np.array_equal(a.view(np.uint32), eng.get_ndarray().view(np.uint32))
+
+
+def test_cuda_array_handoff(native):
+    """CudaArray contract (unittest/test_sapien/test_cuda_array.py:5-92) + aliasing getters."""
+    import torch
+
+    t = torch.tensor([[0, 1, 2], [2, 3, 4]]).float().cuda()
+    arr = native.CudaArray(t)
+    iface = arr.__cuda_array_interface__
+    assert arr.typestr == iface["typestr"] == t.__cuda_array_interface__["typestr"]
+    assert tuple(arr.shape) == iface["shape"] == t.__cuda_array_interface__["shape"]
+    assert tuple(arr.strides) == iface["strides"] == (12, 4)
+    assert arr.ptr == iface["data"][0] == t.data_ptr()
+    assert arr.torch().data_ptr() == t.data_ptr()
+    sl = t[1:, :-1]
+    arr2 = native.CudaArray(sl)
+    assert tuple(arr2.strides) == sl.__cuda_array_interface__["strides"]
+    assert arr2.ptr == sl.data_ptr()
+
+    prm = configs.params("small")
+    left, right = configs.pair(prm, seed=1)
+    eng = make_engine(native, prm)
+    with pytest.raises(RuntimeError, match="No computed data stored"):
+        eng.get_cuda()
+    eng.compute(left, right)
+    out = eng.get_cuda()
+    assert tuple(out.shape) == (prm.rgb_rows, prm.rgb_cols) and tuple(out.strides) == (4 * prm.rgb_cols, 4)
+    assert out.typestr == "f4" and out.cuda_id == torch.cuda.current_device()
+    host = eng.get_ndarray()
+    via_torch = out.torch()
+    via_dlpack = torch.from_dlpack(out.dlpack())
+    via_protocol = torch.from_dlpack(out)
+    for v in (via_torch, via_dlpack, via_protocol):
+        assert v.data_ptr() == out.ptr  # aliases engine memory, no copy
+        assert np.array_equal(v.cpu().numpy().view(np.uint32), host.view(np.uint32))
+    pc = eng.get_point_cloud_cuda()
+    assert tuple(pc.shape) == (prm.rgb_rows * prm.rgb_cols, 3) and tuple(pc.strides) == (12, 4)
+    np.testing.assert_array_equal(pc.torch().cpu().numpy(), eng.get_point_cloud_ndarray())
+
+
+def test_point_cloud_vs_oracle(native, oracle):
+    prm = configs.params("small435")
+    left, right = configs.pair(prm, seed=2)
+    eng = run_ours(native, prm, left, right)
+    depth = eng.get_ndarray()
+    want = oracle.pointcloud(depth, None, prm.main_fx, prm.main_fy, prm.main_skew, prm.main_cx, prm.main_cy)
+    np.testing.assert_allclose(eng.get_point_cloud_ndarray(), want, rtol=1e-4, atol=1e-6)
+
+
+def test_setters_take_effect_next_frame(native, oracle):
+    prm = configs.params("small")
+    left, right = configs.pair(prm, seed=9)
+    eng = make_engine(native, prm, keep_stages=True)
+    eng.compute(left, right)
+    eng.set_penalties(4, 60)
+    eng.set_census_window_size(5, 9)
+    eng.set_matching_block_size(3, 3)
+    eng.set_uniqueness_ratio(30)
+    eng.set_lr_max_diff(2)
+    eng.compute(left, right)
+    new = variant(prm, p1=4, p2=60, census_width=5, census_height=9, bf_width=3, bf_height=3, uniq_ratio=30, lr_max_diff=2)
+    ref = oracle.pipeline(new, left, right)
+    assert_stages_equal(eng, new, ref)
+    with pytest.raises(TypeError):
+        eng.set_penalties(50, 10)
+    with pytest.raises(TypeError):
+        eng.set_census_window_size(4, 4)
+
+
+def test_errors(native):
+    prm = configs.params("small")
+    left, right = configs.pair(prm, seed=1)
+    eng = make_engine(native, prm)
+    with pytest.raises(RuntimeError, match="No computed data stored"):
+        eng.get_ndarray()
+    with pytest.raises(RuntimeError, match="Both images must have the same size"):
+        eng.compute(left, right[:-1])
+    with pytest.raises(RuntimeError, match="Input image size different from initiated"):
+        eng.compute(left[:-1], right[:-1])
+    with pytest.raises(TypeError):
+        eng.compute(left, right, True, 90, 0, 32, 32)  # bbox leaves the image
+    with pytest.raises(TypeError):
+        make_engine(native, variant(prm, max_disp=16))
+    with pytest.raises(TypeError):
+        make_engine(native, variant(prm, mf_size=4))
+
+
+def test_ir_noise_statistics(native):
+    """IR noise (camera.cu:21-75) is statistical: mean ~ I * shape*scale, deterministic per seed,
+    different per frame."""
+    prm = variant(configs.params("small"), rectified=True, speckle_shape=1333.33, speckle_scale=1 / 1333.33,
+                  gaussian_mu=0.0, gaussian_sigma=0.25, mf_size=1)
+    img = np.full((prm.rows, prm.cols), 120, np.uint8)
+    eng = make_engine(native, prm)
+    eng.compute(img, img)
+    a = get_stage(eng, prm, "im0").astype(np.float64)
+    b = get_stage(eng, prm, "im1").astype(np.float64)
+    eng.compute(img, img)
+    a2 = get_stage(eng, prm, "im0").astype(np.float64)
+    assert abs(a.mean() - 120) < 0.5 and abs(b.mean() - 120) < 0.5
+    want_std = np.sqrt((120 ** 2) / 1333.33 + 0.25 ** 2 + 1 / 12)
+    assert abs(a.std() - want_std) < 0.35, (a.std(), want_std)
+    assert not np.array_equal(a, b) and not np.array_equal(a, a2)
+    eng2 = make_engine(native, prm)
+    eng2.compute(img, img)
+    assert np.array_equal(get_stage(eng2, prm, "im0"), a.astype(np.uint8))
