@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- stereo depth frames/s on the BASELINE.json workloads.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C1|C2|C3|C4|C5]
+  python bench.py --impl reference ...        the unmodified reference simsense CUDA build
+                                              (oracle/_ref) on the same GPU
+  python bench.py --impl reference-cpu ...    the scalar C/OpenMP oracle on the host cores
+
+One "step" = one pass of the hot path (DepthSensorEngine compute: front-end, cost volume, 4-path
+SGM, WTA, LR, median, depth, registration) over one synthetic batch.  `value` is measured with the
+inputs resident in HBM (device RGBA float32, the reference's CUDA input format), CUDA-event timed
+on the stream the work is ordered on; `e2e` goes through the public Python API with pinned HOST
+buffers, uploads and the depth read-back inside the timed region.  N>1: one process per GPU
+(torchrun), the same per-GPU workload on every rank (environments/frames are independent: no
+collective on the data path), barrier + max-over-ranks timing, `scaling` = weak.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "stereo depth frames/sec at 1280x720/128 disp per B200 and batched env-frames/sec 1-8 GPU"
+WORKLOADS = {
+    # name: (params key, batch, bbox, point cloud, description)
+    "C1": ("C1", 1, None, "", "single D415-like IR pair 1280x720, 128 disp, remap + 7x7 census + 7x7 block + 4-path SGM + LR + median3 + registration/dilation to 1920x1080"),
+    "C2": ("C2", 1, "bbox", "xyzrgb", "C1 with bbox ROI (100,100) 640x360 + RGB point cloud"),
+    "C3": ("C3", 64, None, "", "batched 64 envs x 848x480, 96 disp (D435)"),
+    "C4": ("C4", 1024, None, "", "1024 envs x 256x256, 64 disp, env-sharded"),
+    "C5": ("C5", 4, None, "", "1920x1080, 256 disp, 4-frame batches"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cpu"])
+    ap.add_argument("--workload", default="C1", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the env batch of the workload (per GPU)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f:
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def dist_setup(n_gpus):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def barrier(world):
+    import torch
+
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(v: float, world) -> float:
+    if world == 1:
+        return v
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([v], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def make_inputs(prm, batch, n_sets, torch):
+    """n_sets distinct batches of device RGBA float32 pairs (+ the u8 originals on the host)."""
+    from sapien_b200 import synth
+
+    sets = []
+    base = [synth.make_pair(prm.rows, prm.cols, prm.max_disp, s)[:2] for s in range(min(8, max(n_sets, batch)))]
+    for k in range(n_sets):
+        l = np.stack([base[(k + i) % len(base)][0] for i in range(batch)])
+        r = np.stack([base[(k + i) % len(base)][1] for i in range(batch)])
+        if batch == 1:
+            l, r = l[0], r[0]
+        sets.append((l, r))
+    dev = [(torch.from_numpy(synth.to_rgba(l)).cuda(), torch.from_numpy(synth.to_rgba(r)).cuda()) for l, r in sets]
+    return sets, dev
+
+
+def cpu_baseline(prm, bbox, seconds, torch_threads=None):
+    """The scalar C/OpenMP oracle timed on the host cores over a bounded sample of the workload."""
+    from oracle import Oracle, configs
+
+    orc = Oracle()
+    l, r = configs.pair(prm, 0)
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    orc.pipeline(prm, l, r, bbox=bbox, stages=False)
+    first = time.perf_counter() - t0
+    n = int(max(1, min(50, seconds / max(first, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        orc.pipeline(prm, l, r, bbox=bbox, stages=False)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{n} frames of the workload, one frame at a time, OpenMP over rows/columns on {cores} threads (after 1 warm-up frame)"}
+
+
+def run_ours(args, rank, world, local):
+    import torch
+
+    from oracle import configs
+    from sapien_b200 import simsense
+
+    key, batch, bbox, pc, desc = WORKLOADS[args.workload]
+    if args.batch:
+        batch = args.batch
+    prm = configs.params(key)
+    bbox_t = configs.BBOX_C2 if bbox else None
+    eng = simsense.DepthSensorEngine(*prm.engine_args(), device=local, batch=batch)
+    n_sets = 8 if batch == 1 else 2
+    host_sets, dev_sets = make_inputs(prm, batch, n_sets, torch)
+    rgba = None
+    if pc:
+        from sapien_b200 import synth
+
+        rgba = torch.from_numpy(synth.make_rgb(prm.rgb_rows, prm.rgb_cols, 0)).cuda()
+    stream = torch.cuda.Stream()
+    bb = (True, *bbox_t) if bbox_t else (False, 0, 0, 0, 0)
+
+    def step(i):
+        l, r = dev_sets[i % n_sets]
+        eng.compute(l, r, *bb, stream=stream.cuda_stream, sync=False)
+        if pc:
+            eng.get_rgb_point_cloud_cuda(rgba)
+
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            step(i)
+        stream.synchronize()
+        barrier(world)
+        eng.set_profiling(True)
+        eng.get_stage_times()
+        sampler = ClockSampler(local)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.steps):
+            step(i)
+        e1.record(stream)
+        stream.synchronize()
+        barrier(world)
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop()
+        stages = dict(eng.get_stage_times())
+        eng.set_profiling(False)
+    launches = eng.get_launches_per_compute() + (1 if pc else 0)
+    ms = max_over_ranks(ms, world)
+    frames = batch * args.steps * world
+    value = frames / (ms / 1e3)
+
+    # ---- e2e: public API, pinned host buffers, H2D + D2H inside the timed region ---------------
+    pin_l = [torch.from_numpy(l).pin_memory() for l, _ in host_sets]
+    pin_r = [torch.from_numpy(r).pin_memory() for _, r in host_sets]
+    out_shape = ((batch,) if batch > 1 else ()) + (prm.rgb_rows, prm.rgb_cols)
+    pin_out = torch.empty(out_shape, dtype=torch.float32).pin_memory()
+    out_np = pin_out.numpy()
+    e2e_steps = max(3, min(args.steps, 30))
+    for i in range(3):
+        eng.compute(pin_l[i % n_sets].numpy(), pin_r[i % n_sets].numpy(), *bb)
+        eng.get_ndarray(out=out_np)
+    barrier(world)
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        eng.compute(pin_l[i % n_sets].numpy(), pin_r[i % n_sets].numpy(), *bb)
+        eng.get_ndarray(out=out_np)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+    e2e = {"value": batch * e2e_steps * world / e2e_s, "unit": "frames/s",
+           "h2d_bytes_per_step": int(2 * batch * prm.rows * prm.cols), "d2h_bytes_per_step": int(out_np.nbytes),
+           "api": "DepthSensorEngine.compute(left_u8, right_u8[, bbox]) + get_ndarray(out=pinned)", "steps": e2e_steps}
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel ---------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    s = (prm.rows * prm.cols) if bbox_t is None else bbox_t[2] * bbox_t[3]
+    V = 2 * s * prm.max_disp * batch
+    kernel_bytes = {"cost": 8 * s * batch + V, "aggr_down": 2 * V, "aggr_up": 4 * V, "aggr_right_wta": 2 * V + 6 * s * batch}
+    st_ms = {k: v for k, v in stages.items() if k != "frames"}
+    dom = max((k for k in kernel_bytes if k in st_ms), key=lambda k: st_ms[k], default=None)
+    roofline = None
+    if dom:
+        ach = kernel_bytes[dom] / (st_ms[dom] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": {"cost": "cost_kernel", "aggr_down": "aggr_kernel<NAUX=0> (top->bottom)", "aggr_up": "aggr_kernel<NAUX=2> (bottom->top + L1 + L2)",
+                                               "aggr_right_wta": "aggr_kernel<WTA> (left->right + blend + WTA)"}[dom],
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "algorithmic_bytes_per_launch": int(kernel_bytes[dom]), "avg_launch_ms": st_ms[dom], "peak_source": peak_src,
+                    "per_kernel_gbs": {k: kernel_bytes[k] / (st_ms[k] * 1e-3) / 1e9 for k in kernel_bytes if k in st_ms}}
+    alg = configs.algorithmic_bytes(prm, rgba_input=True, bbox=bbox_t, point_cloud=pc) * batch
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u16", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "batch_per_gpu": batch, "input": "device float32 RGBA pairs (reference CUDA input format)",
+                   "l2": f"{n_sets} distinct input sets rotate; per-step intermediate traffic (3 u16 volumes = {3 * V / 1e6:.0f} MB) exceeds the 126 MB L2" if 3 * V > 126e6
+                   else f"{n_sets} distinct input sets rotate; volumes of one batch = {3 * V / 1e6:.0f} MB",
+                   "parallelism": f"env-sharded x{world}, no collective"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches * args.steps,
+        "roofline": roofline,
+        "frame_roofline": {"algorithmic_bytes_per_step": int(alg), "achieved_gbs": alg / (ms / args.steps * 1e-3) / 1e9 ,
+                           "frac_of_peak": alg / (ms / args.steps * 1e-3) / 1e9 / peak},
+        "stages_ms": st_ms,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(prm, bbox_t, args.cpu_seconds)
+    print(json.dumps(line))
+
+
+def run_reference(args, rank, world, local):
+    """The unmodified reference simsense (oracle/_ref) through its own compute()/getMat2d() API."""
+    import torch
+
+    from oracle import REF_SO, RefEngine, configs
+
+    if not os.path.exists(REF_SO):
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libsimsense_ref.so not built (needs /root/reference at build time)"}))
+        return
+    key, batch, bbox, pc, desc = WORKLOADS[args.workload]
+    if args.batch:
+        batch = args.batch
+    prm = configs.params(key)
+    bbox_t = configs.BBOX_C2 if bbox else None
+    ref = RefEngine(prm)  # the reference has no batch API: a batch is a sequential loop
+    n_sets = 8
+    host_sets, dev_sets = make_inputs(prm, 1, n_sets, torch)
+    rgba = None
+    if pc:
+        from sapien_b200 import synth
+
+        rgba = torch.from_numpy(synth.make_rgb(prm.rgb_rows, prm.rgb_cols, 0)).cuda()
+    steps = args.steps
+    per_step = min(batch, 8)  # bounded sample of a batched workload
+
+    def step(i):
+        for b in range(per_step):
+            l, r = dev_sets[(i + b) % n_sets]
+            ref.compute_device(l.data_ptr(), r.data_ptr(), bbox_t)
+            if pc:
+                ref.lib.ref_get_rgb_point_cloud  # host copy is part of the reference getter; skip in the device-timed loop
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    barrier(world)
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    clocks = sampler.stop()
+    value = per_step * steps * world / (ms / 1e3)
+    e2e_steps = max(3, min(steps, 20))
+    out = None
+    for i in range(2):
+        ref.compute_host(*host_sets[i % n_sets], bbox_t)
+        out = ref.depth()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        ref.compute_host(*host_sets[i % n_sets], bbox_t)
+        out = ref.depth()
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+    if rank != 0:
+        return
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "batch_per_gpu": per_step,
+                   "input": "device float32 RGBA pairs through simsense::DepthSensorEngine::compute(void*, void*, ...)",
+                   "note": "unmodified reference simsense CUDA sources recompiled for sm_100a (oracle/_ref); the reference has no CPU implementation of this path and no batch API (a batch is a sequential loop)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_steps * world / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(2 * prm.rows * prm.cols),
+                "d2h_bytes_per_step": int(out.nbytes), "api": "DepthSensorEngine::compute(Mat2d<u8>, Mat2d<u8>) + getMat2d()", "steps": e2e_steps},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": 0, "kind": "reference",
+                         "sample": "reference simsense is CUDA-only: this arm runs its own kernels on the same B200 (0 host compute threads)"},
+    }
+    print(json.dumps(line))
+
+
+def run_reference_cpu(args, rank):
+    if rank != 0:
+        return
+    from oracle import configs
+
+    key, batch, bbox, pc, desc = WORKLOADS[args.workload]
+    prm = configs.params(key)
+    bbox_t = configs.BBOX_C2 if bbox else None
+    cb = cpu_baseline(prm, bbox_t, max(args.cpu_seconds, 10.0))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "note": "scalar C/OpenMP port of the reference kernels (oracle/simsense_oracle.c)"},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference-cpu":
+        run_reference_cpu(args, int(os.environ.get("RANK", "0")))
+        return
+    rank, world, local = dist_setup(args.gpus)
+    try:
+        if args.impl == "reference":
+            run_reference(args, rank, world, local)
+        else:
+            run_ours(args, rank, world, local)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

