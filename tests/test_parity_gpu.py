@@ -10,6 +10,7 @@ import pytest
 
 from oracle import REF_SO, RefEngine, configs
 from sapien_b200 import synth
+from tests import golden_util
 from tests.common import (assert_depth_close, assert_stages_equal, get_stage, make_engine, variant)
 
 pytestmark = pytest.mark.gpu
@@ -95,6 +96,20 @@ def test_small_bbox_vs_oracle(native, oracle, bbox):
     eng = run_ours(native, prm, left, right, bbox=bbox, keep_stages=True)
     assert_stages_equal(eng, prm, ref, bbox=bbox)
     assert_depth_close(eng.get_ndarray(), ref["out"])
+
+
+@pytest.mark.parametrize("case", golden_util.cases())
+def test_cuda_engine_vs_reference_golden(native, case):
+    """The CUDA engine against the committed outputs of the unmodified reference simsense kernels
+    (tests/golden/, captured on a B200): integer stages bit-exact (volumes by SHA-256), float
+    stages bit-exact except at the reference's own race pixels, final depth within 1e-4."""
+    g = golden_util.Golden(case)
+    eng = run_ours(native, g.params, g.left, g.right, bbox=g.bbox, keep_stages=True)
+    names = ["census0", "census1", "cost", "L0", "L1", "L2", "LAll", "disp_right", "disp_lr", "disp_med", "depth"]
+    stages = {n: get_stage(eng, g.params, n, g.bbox) for n in names}
+    golden_util.check_against_golden(g, stages, eng.get_ndarray(), f"cuda[{case}]")
+    fast = run_ours(native, g.params, g.left, g.right, bbox=g.bbox)
+    assert np.array_equal(fast.get_ndarray().view(np.uint32), eng.get_ndarray().view(np.uint32))
 
 
 needs_ref = pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/libsimsense_ref.so not built")
