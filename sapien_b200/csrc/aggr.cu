@@ -6,22 +6,25 @@
 // organisation is new:
 //
 //  * one WARP walks one path (an image row or column); a lane owns DPL = 2*NR consecutive
-//    disparities packed as u16x2 registers, so a path step is ~25 instructions and needs no
-//    shared memory, no __syncthreads and no atomics (the reference spends 3 barriers and one
-//    shared atomicMin per step with one thread per disparity);
-//  * d-1 / d+1 neighbours come from funnel shifts inside the lane plus one shuffle each way;
-//    the running minimum is one redux.sync; the min/add chain is Blackwell DPX
-//    (__viaddmin_u16x2 -> VIADDMNMX.U16x2, __vminu2 -> VIMNMX.U16x2);
-//  * the cost volume is streamed through a per-warp shared-memory ring filled by cp.async
-//    (LDGSTS) PF path steps ahead and retired with cp.async.wait_group, so a warp keeps
-//    PF*(1+NAUX) independent 256 B (D=128) requests in flight: the walk is latency-hidden and the
-//    pass becomes HBM-bound instead of barrier-bound.  (A register prefetch ring does not work:
-//    the 6 scoreboard slots alias loads issued 6 steps apart, measured 1 DRAM latency per step.);
+//    disparities packed as u16x2 registers.  A path step is ~25 instructions and needs no
+//    __syncthreads and no atomics (the reference: one thread per disparity, 3 barriers and one
+//    shared atomicMin per step);
+//  * d-1 / d+1 neighbours: funnel shifts inside the lane, one shuffle each way across lanes, and a
+//    per-lane byte-permute selector that folds the d=0 / d=D-1 border rule into the same PRMT;
+//    the running minimum is vmin + half-swap + ONE redux.sync (CREDUX) that already returns
+//    m|m<<16; the min/add chain is Blackwell DPX (VIADDMNMX.U16x2, VIMNMX.U16x2, VIMNMX3.U16x2);
+//  * the cost volume (and the partial sums of earlier passes) are streamed into shared memory by
+//    the bulk-copy engine (cp.async.bulk / UBLKCP, completion on an mbarrier) in chunks of K path
+//    steps, NCH chunks deep per warp: one 4 KB request per chunk for horizontal paths, K row
+//    pieces issued by K lanes at once for vertical ones.  No per-step address arithmetic, no
+//    LDGSTS issue cost; a warp keeps (NCH-1)*K*D*2 bytes per stream in flight;
 //  * pass order is  (right->left || top->bottom)  ->  bottom->top (+L1+L2)  ->  left->right.
-//    The last pass holds LAll(y,x,:) = (L0+L1+L2+L3)/4 in registers and does the winner-takes-all
-//    in place: left disparity (uniqueness, sub-pixel) per step, right disparity through a
-//    register recurrence along the diagonal  T_x(d) = min(T_{x-1}(d-1), LAll(x,d)).  LAll is never
-//    written to memory (the reference writes it and launches one block per pixel to read it back).
+//    The last pass forms LAll(y,x,:) = (L0+L1+L2+L3)/4 in registers.  Per step it only records the
+//    packed (min,argmin) key and advances the right-disparity recurrence along the diagonal,
+//    T_x(d) = min(T_{x-1}(d-1), LAll(x,d)); the LAll row goes to a 32-pixel shared tile and every 32
+//    steps the warp switches to ONE LANE PER PIXEL for uniqueness + sub-pixel (packed 3-input
+//    min scan of the row with the d*-1..d*+1 window masked), so the winner-takes-all costs ~4
+//    instructions per pixel instead of a block per pixel.  LAll is never written to HBM.
 //
 // HBM traffic: 2V + 2V + 4V + 2V = 10 V for aggregation + WTA, against ~13 V in the reference
 // (V = one u16 volume).
@@ -33,69 +36,43 @@ namespace ssb {
 struct AggrArgs {
   const uint16_t *C;
   const uint16_t *aux0, *aux1;
-  uint16_t *out;  // plain passes: L ; up pass: L+aux0+aux1
-  uint16_t *dbg0; // up pass: L3 ; wta pass: L0
-  uint16_t *dbg1; // wta pass: LAll
+  uint16_t *out;  // MODE 0: L ; MODE 1: L+aux0+aux1
+  uint16_t *dbg0; // MODE 1: L3 ; MODE 2: L0      (keep_stages only)
+  uint16_t *dbg1; // MODE 2: LAll                 (keep_stages only)
   float *dispL;
   uint16_t *dispR;
   int N, rows, cols, D;
   int vertical, reverse;
-  uint32_t P1P1, P2P2, BIG;
+  uint32_t P1P1, P2P2;
   int uniq;
 };
 
-template <int NR>
-__device__ __forceinline__ void sgm_step(uint32_t (&L)[NR], const uint32_t (&c)[NR], uint32_t P1P1,
-                                         uint32_t P2P2, uint32_t BIG, bool first_lane,
-                                         bool last_lane, bool active) {
-  // running minimum over all disparities of the previous pixel
-  uint32_t mn = L[0];
-#pragma unroll
-  for (int j = 1; j < NR; ++j) mn = __vminu2(mn, L[j]);
-  const uint32_t m = __reduce_min_sync(FULL, min_halves(mn));
-  const uint32_t mm = pack2(m);
-  const uint32_t mP2 = mm + P2P2;
-  // d-1 of my first element lives in the previous lane, d+1 of my last in the next lane
-  uint32_t up = __shfl_up_sync(FULL, L[NR - 1], 1);
-  uint32_t dn = __shfl_down_sync(FULL, L[0], 1);
-  if (first_lane) up = BIG << 16;
-  if (last_lane) dn = BIG;
-  uint32_t nl[NR];
-#pragma unroll
-  for (int j = 0; j < NR; ++j) {
-    const uint32_t lo = (j == 0) ? up : L[j - 1];
-    const uint32_t hi = (j == NR - 1) ? dn : L[j + 1];
-    const uint32_t lm1 = __funnelshift_l(lo, L[j], 16); // L(d-1) for both halves
-    const uint32_t lp1 = __funnelshift_r(L[j], hi, 16); // L(d+1) for both halves
-    uint32_t t = __viaddmin_u16x2(lm1, P1P1, L[j]);
-    t = __viaddmin_u16x2(lp1, P1P1, t);
-    t = __vminu2(t, mP2);
-    nl[j] = t - mm + c[j]; // per-half: t >= m and result < 65536 in the fast regime
-  }
-  const uint32_t bigbig = pack2(BIG);
-#pragma unroll
-  for (int j = 0; j < NR; ++j) L[j] = active ? nl[j] : bigbig;
+// ---- mbarrier + bulk-copy (TMA 1-D) primitives -------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// ---- cp.async (LDGSTS) staging: every lane copies its own NR words global -> shared ------------
-template <int NR> __device__ __forceinline__ void cp_async_vec(uint32_t saddr, const uint16_t *g) {
+template <int NR> __device__ __forceinline__ void lds_vec(const void *p, uint32_t (&r)[NR]) {
   if constexpr (NR == 1) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
-  } else if constexpr (NR == 2) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(g) : "memory");
-  } else {
-#pragma unroll
-    for (int i = 0; i < NR / 4; ++i)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr + 16 * i), "l"(g + 8 * i) : "memory");
-  }
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-template <int NR> __device__ __forceinline__ void lds_vec(const uint32_t *p, uint32_t (&r)[NR]) {
-  if constexpr (NR == 1) {
-    r[0] = p[0];
+    r[0] = *reinterpret_cast<const uint32_t *>(p);
   } else if constexpr (NR == 2) {
     const uint2 v = *reinterpret_cast<const uint2 *>(p);
     r[0] = v.x; r[1] = v.y;
@@ -107,190 +84,322 @@ template <int NR> __device__ __forceinline__ void lds_vec(const uint32_t *p, uin
     }
   }
 }
-
-// Shared memory per warp: (1+NAUX) streams x (PF+1) slots x 32 lanes x NR words, then (WTA) D u16.
-template <int NR, int NAUX, int PF> constexpr size_t ring_bytes_per_warp() {
-  return (size_t)(1 + NAUX) * (PF + 1) * 32 * NR * 4;
+template <int NR> __device__ __forceinline__ void st_vec(void *p, const uint32_t (&r)[NR]) {
+  if constexpr (NR == 1) {
+    *reinterpret_cast<uint32_t *>(p) = r[0];
+  } else if constexpr (NR == 2) {
+    *reinterpret_cast<uint2 *>(p) = make_uint2(r[0], r[1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NR / 4; ++i)
+      reinterpret_cast<uint4 *>(p)[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+  }
 }
 
-template <int NR, int NAUX, bool WTA, int PF>
-__global__ void __launch_bounds__(256) aggr_kernel(const AggrArgs a) {
+// One SGM path step on packed u16x2 registers (aggr.cu:39-76 of the reference):
+//   L'(d) = C(d) + min(L(d), L(d-1)+P1, L(d+1)+P1, m+P2) - m,   m = min_k L(k).
+// selUp / selDn are per-lane PRMT selectors: 0x5432 = take the neighbour lane's half, 0x5454 /
+// 0x3232 (first / last disparity) = repeat the own value, which makes the missing neighbour
+// harmless (L(d)+P1 never beats L(d)).  L == 0 everywhere reproduces the first-pixel rule L = C.
+template <int NR>
+__device__ __forceinline__ void sgm_step(uint32_t (&L)[NR], const uint32_t (&c)[NR], uint32_t P1P1,
+                                         uint32_t P2P2, uint32_t selUp, uint32_t selDn) {
+  uint32_t t = L[0];
+#pragma unroll
+  for (int j = 1; j < NR; ++j) t = __vminu2(t, L[j]);
+  t = __vminu2(t, __byte_perm(t, t, 0x1032));        // both halves = lane minimum
+  const uint32_t mm = __reduce_min_sync(FULL, t);     // m | m << 16
+  const uint32_t mP2 = mm + P2P2;
+  const uint32_t up = __shfl_up_sync(FULL, L[NR - 1], 1);
+  const uint32_t dn = __shfl_down_sync(FULL, L[0], 1);
+  uint32_t nl[NR];
+#pragma unroll
+  for (int j = 0; j < NR; ++j) {
+    const uint32_t lm1 = (j == 0) ? __byte_perm(up, L[0], selUp) : __funnelshift_l(L[j - 1], L[j], 16);
+    const uint32_t lp1 = (j == NR - 1) ? __byte_perm(L[NR - 1], dn, selDn) : __funnelshift_r(L[j], L[j + 1], 16);
+    uint32_t v = __viaddmin_u16x2(lm1, P1P1, L[j]);
+    v = __viaddmin_u16x2(lp1, P1P1, v);
+    v = __vminu2(v, mP2);
+    nl[j] = v - mm + c[j]; // per half: v >= m, and the sum stays below 65536 in the fast regime
+  }
+#pragma unroll
+  for (int j = 0; j < NR; ++j) L[j] = nl[j];
+}
+
+// MODE 0: plain path (out = L).  MODE 1: out = L + aux0 + aux1.  MODE 2: left->right path,
+// LAll = (L + aux0)/4, winner-takes-all (horizontal forward only).
+template <int MODE> __host__ __device__ constexpr int nstream() { return MODE == 0 ? 1 : (MODE == 1 ? 3 : 2); }
+
+struct AggrSmem { // per-warp layout (bytes); PIECE = D*2
+  int ring, tile, gk, rb, total;
+};
+template <int MODE, int K, int NCH> __host__ __device__ inline AggrSmem aggr_smem(int D) {
+  AggrSmem s;
+  const int piece = D * 2;
+  s.ring = 64; // NCH mbarriers first (NCH <= 8)
+  s.tile = s.ring + nstream<MODE>() * NCH * K * piece;
+  s.gk = s.tile + (MODE == 2 ? 32 * (piece + 16) : 0);
+  s.rb = s.gk + (MODE == 2 ? 32 * 4 : 0);
+  s.total = s.rb + (MODE == 2 ? 32 * 2 : 0);
+  s.total = (s.total + 127) & ~127;
+  return s;
+}
+
+template <int NR, int MODE, bool PARTIAL, int K, int NCH>
+__global__ void __launch_bounds__(128) aggr_kernel(const AggrArgs a) {
   constexpr int DPL = 2 * NR;
-  constexpr int NSLOT = PF + 1;             // prefetch distance PF, one spare slot (no WAR hazard)
-  constexpr int SLOT_WORDS = 32 * NR;
-  constexpr int STREAM_WORDS = NSLOT * SLOT_WORDS;
-  extern __shared__ __align__(16) uint32_t smem[];
+  constexpr int NS = nstream<MODE>();
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
   const long path = (long)blockIdx.x * wpb + warp;
   const int per_env = a.vertical ? a.cols : a.rows;
-  if (path >= (long)a.N * per_env) return;
+  if (path >= (long)a.N * per_env) return; // warps are independent: no block-level barrier anywhere
   const int n = (int)(path / per_env);
   const int q = (int)(path - (long)n * per_env);
   const int steps = a.vertical ? a.rows : a.cols;
-  const size_t D = (size_t)a.D;
-  const size_t env = (size_t)n * a.rows * a.cols * D;
-  size_t base;
-  long stride;
-  if (a.vertical) { stride = (long)a.cols * (long)D; base = env + (size_t)q * D; }
-  else { stride = (long)D; base = env + (size_t)q * a.cols * D; }
-  if (a.reverse) { base += (size_t)(steps - 1) * (size_t)stride; stride = -stride; }
-  const int d0 = lane * DPL;
-  const bool active = d0 < a.D;
-  const bool first_lane = lane == 0;
-  const bool last_lane = lane == a.D / DPL - 1;
-  base += active ? d0 : 0;
-  const uint16_t *pC = a.C + base;
-  const uint16_t *pA0 = NAUX > 0 ? a.aux0 + base : nullptr;
-  const uint16_t *pA1 = NAUX > 1 ? a.aux1 + base : nullptr;
-  const uint32_t bigbig = pack2(a.BIG);
+  const int D = a.D;
+  const int PIECE = D * 2;
+  const AggrSmem lay = aggr_smem<MODE, K, NCH>(D);
+  unsigned char *wsm = smem_raw + (size_t)warp * lay.total;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(wsm);
+  unsigned char *ring = wsm + lay.ring;
+  const uint32_t ring_s = bar0 + lay.ring;
+  const int STREAM = NCH * K * PIECE; // bytes per stream in the ring
 
-  uint32_t *ring = smem + (size_t)warp * ((1 + NAUX) * STREAM_WORDS) + lane * NR;
-  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
-  auto issue = [&](int step, int slot) {
-    const long off = (long)step * stride;
-    cp_async_vec<NR>(ring_s + (uint32_t)(slot * SLOT_WORDS * 4), pC + off);
-    if (NAUX > 0) cp_async_vec<NR>(ring_s + (uint32_t)((STREAM_WORDS + slot * SLOT_WORDS) * 4), pA0 + off);
-    if (NAUX > 1) cp_async_vec<NR>(ring_s + (uint32_t)((2 * STREAM_WORDS + slot * SLOT_WORDS) * 4), pA1 + off);
-  };
+  // byte offset of path step 0, disparity 0, and the signed byte stride between steps
+  const size_t env = (size_t)n * a.rows * a.cols * D;
+  size_t e0 = env + (a.vertical ? (size_t)q * D : (size_t)q * a.cols * D);
+  long sstride = a.vertical ? (long)a.cols * D * 2 : (long)PIECE;
+  if (a.reverse) { e0 += (size_t)(steps - 1) * (size_t)(sstride / 2); sstride = -sstride; }
+  const char *gC = reinterpret_cast<const char *>(a.C + e0);
+  const char *gA0 = NS > 1 ? reinterpret_cast<const char *>(a.aux0 + e0) : nullptr;
+  const char *gA1 = NS > 2 ? reinterpret_cast<const char *>(a.aux1 + e0) : nullptr;
+
+  const int nact = D / DPL; // active lanes
+  const bool active = !PARTIAL || lane < nact;
+  const int loff = lane * NR * 4; // byte offset of this lane inside a piece
+  const uint32_t selUp = lane == 0 ? 0x5454u : 0x5432u;
+  const uint32_t selDn = lane == nact - 1 ? 0x3232u : 0x5432u;
+  const bool hrev = !a.vertical && a.reverse; // chunk lies in memory in descending step order
+
+  if (lane == 0) {
 #pragma unroll
-  for (int j = 0; j < PF; ++j) {
-    if (active && j < steps) issue(j, j);
-    cp_async_commit();
+    for (int i = 0; i < NCH; ++i) mbar_init(bar0 + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  __syncwarp();
+
+  const int nchunks = (steps + K - 1) / K;
+  auto issue = [&](int ci) {
+    const int slot = ci % NCH;
+    const int s0 = ci * K;
+    const int kc = min(K, steps - s0);
+    const uint32_t bar = bar0 + 8 * slot;
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(kc * PIECE * NS));
+    __syncwarp();
+    const uint32_t dst = ring_s + (uint32_t)(slot * K * PIECE);
+    if (a.vertical) {
+      if (lane < kc) {
+        const long off = (long)(s0 + lane) * sstride;
+        const uint32_t d = dst + (uint32_t)(lane * PIECE);
+        bulk_g2s(d, gC + off, (uint32_t)PIECE, bar);
+        if (NS > 1) bulk_g2s(d + STREAM, gA0 + off, (uint32_t)PIECE, bar);
+        if (NS > 2) bulk_g2s(d + 2 * STREAM, gA1 + off, (uint32_t)PIECE, bar);
+      }
+    } else if (lane == 0) {
+      const long off = (long)(hrev ? s0 + kc - 1 : s0) * sstride;
+      const uint32_t bytes = (uint32_t)(kc * PIECE);
+      bulk_g2s(dst, gC + off, bytes, bar);
+      if (NS > 1) bulk_g2s(dst + STREAM, gA0 + off, bytes, bar);
+      if (NS > 2) bulk_g2s(dst + 2 * STREAM, gA1 + off, bytes, bar);
+    }
+  };
+  for (int ci = 0; ci < NCH - 1 && ci < nchunks; ++ci) issue(ci);
 
   uint32_t L[NR];
 #pragma unroll
-  for (int r = 0; r < NR; ++r) L[r] = bigbig;
+  for (int r = 0; r < NR; ++r) L[r] = active ? 0u : 0xffffffffu;
 
-  // winner-takes-all state (left->right pass only)
-  uint32_t T[DPL];
+  // output cursors (bytes)
+  char *pOut = MODE != 2 ? reinterpret_cast<char *>(a.out + e0) + loff : nullptr;
+  char *pDbg0 = a.dbg0 ? reinterpret_cast<char *>(a.dbg0 + e0) + loff : nullptr;
+  char *pDbg1 = (MODE == 2 && a.dbg1) ? reinterpret_cast<char *>(a.dbg1 + e0) + loff : nullptr;
+
+  // ---- winner-takes-all state (MODE 2) ----------------------------------------------------------
+  uint32_t T[DPL], dconst[NR];
 #pragma unroll
   for (int k = 0; k < DPL; ++k) T[k] = 0xffffffffu;
-  uint16_t *my_la = reinterpret_cast<uint16_t *>(smem + (size_t)wpb * ((1 + NAUX) * STREAM_WORDS)) + (size_t)warp * a.D;
-  const size_t rowpix = WTA ? ((size_t)n * a.rows + q) * a.cols : 0;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) dconst[r] = (uint32_t)(lane * DPL + 2 * r) | ((uint32_t)(lane * DPL + 2 * r + 1) << 16);
+  const int TP = PIECE + 16; // tile row pitch: lanes of the per-pixel phase hit distinct banks
+  unsigned char *tile = wsm + lay.tile;
+  uint32_t *gkbuf = reinterpret_cast<uint32_t *>(wsm + lay.gk);
+  uint16_t *rbuf = reinterpret_cast<uint16_t *>(wsm + lay.rb);
+  const size_t rowpix = MODE == 2 ? ((size_t)n * a.rows + q) * a.cols : 0;
   const int k100u = 100 - a.uniq;
+  const uint32_t firstmask = lane == 0 ? 0xffffffffu : 0u;
+  const bool last_lane = lane == nact - 1;
 
-  int slot = 0, fill = PF;
-  for (int s = 0; s < steps; ++s) {
-    cp_async_wait<PF - 1>(); // the group of step s has landed
+  auto step = [&](int s, const unsigned char *pc) {
     uint32_t c[NR], x0[NR], x1[NR];
-#pragma unroll
-    for (int r = 0; r < NR; ++r) { c[r] = 0; x0[r] = 0; x1[r] = 0; }
     if (active) {
-      lds_vec<NR>(ring + slot * SLOT_WORDS, c);
-      if (NAUX > 0) lds_vec<NR>(ring + STREAM_WORDS + slot * SLOT_WORDS, x0);
-      if (NAUX > 1) lds_vec<NR>(ring + 2 * STREAM_WORDS + slot * SLOT_WORDS, x1);
-      if (s + PF < steps) issue(s + PF, fill); // refills the slot consumed one step ago
-    }
-    cp_async_commit();
-    slot = slot + 1 == NSLOT ? 0 : slot + 1;
-    fill = fill + 1 == NSLOT ? 0 : fill + 1;
-    if (s == 0) {
-#pragma unroll
-      for (int r = 0; r < NR; ++r) L[r] = active ? c[r] : bigbig;
+      lds_vec<NR>(pc, c);
+      if (NS > 1) lds_vec<NR>(pc + STREAM, x0);
+      if (NS > 2) lds_vec<NR>(pc + 2 * STREAM, x1);
     } else {
-      sgm_step<NR>(L, c, a.P1P1, a.P2P2, a.BIG, first_lane, last_lane, active);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) { c[r] = 0; x0[r] = 0; x1[r] = 0; }
     }
-    const long off = (long)s * stride;
-    if (!WTA) {
+    sgm_step<NR>(L, c, a.P1P1, a.P2P2, selUp, selDn);
+    if (PARTIAL) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) L[r] = active ? L[r] : 0xffffffffu;
+    }
+    if (MODE != 2) {
       if (active) {
-        uint32_t o[NR];
+        if (MODE == 0) {
+          st_vec<NR>(pOut, L);
+        } else {
+          uint32_t o[NR];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) o[r] = L[r] + (NAUX > 0 ? x0[r] : 0u) + (NAUX > 1 ? x1[r] : 0u);
-        Vec<NR>::st(a.out + base + off, o);
-        if (NAUX > 0 && a.dbg0) Vec<NR>::st(a.dbg0 + base + off, L);
+          for (int r = 0; r < NR; ++r) o[r] = L[r] + x0[r] + x1[r];
+          st_vec<NR>(pOut, o);
+          if (pDbg0) { st_vec<NR>(pDbg0, L); }
+        }
       }
+      pOut += sstride;
+      if (MODE == 1 && pDbg0) pDbg0 += sstride;
     } else {
-      // ---- blend: LAll = (L0 + (L1+L2+L3)) / 4, per 16-bit half ---------------------------
+      // ---- blend: LAll = (L0 + (L1+L2+L3)) / 4 per 16-bit half (aggr.cu:192,222) ---------------
       uint32_t la[NR];
 #pragma unroll
       for (int r = 0; r < NR; ++r) la[r] = ((L[r] + x0[r]) >> 2) & 0x3fff3fffu;
+      unsigned char *trow = tile + (s & 31) * TP;
       if (active) {
-        if (a.dbg0) Vec<NR>::st(a.dbg0 + base + off, L);
-        if (a.dbg1) Vec<NR>::st(a.dbg1 + base + off, la);
-        Vec<NR>::st(my_la + d0, la);
+        st_vec<NR>(trow + loff, la);
+        if (pDbg0) { st_vec<NR>(pDbg0, L); st_vec<NR>(pDbg1, la); }
       }
-      // ---- keys (value<<16 | d): u32 min == lowest value, then lowest d -----------------
+      if (pDbg0) { pDbg0 += sstride; pDbg1 += sstride; }
+      // ---- keys (value << 16 | d): u32 min == lowest value, then lowest d (wta.cu:30-65) -------
       uint32_t key[DPL];
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
-        key[2 * r] = active ? ((la[r] << 16) | (uint32_t)(d0 + 2 * r)) : 0xffffffffu;
-        key[2 * r + 1] = active ? ((la[r] & 0xffff0000u) | (uint32_t)(d0 + 2 * r + 1)) : 0xffffffffu;
+        key[2 * r] = active ? __byte_perm(la[r], dconst[r], 0x1054) : 0xffffffffu;
+        key[2 * r + 1] = active ? __byte_perm(la[r], dconst[r], 0x3276) : 0xffffffffu;
       }
       uint32_t lk = key[0];
 #pragma unroll
       for (int k = 1; k < DPL; ++k) lk = min(lk, key[k]);
       const uint32_t gk = __reduce_min_sync(FULL, lk);
-      const int mval = (int)(gk >> 16);
-      const int dstar = (int)(gk & 0xffffu);
-      // ---- uniqueness (wta.cu:203): all d: LAll(d)*(100-u) >= m*100 or |d-d*|<=1 ---------
-      bool uniq_ok;
-      if (k100u > 0) {
-        uint32_t m2 = 0xffffu; // smallest value outside d*-1..d*+1 (the test is monotone)
-#pragma unroll
-        for (int k = 0; k < DPL; ++k) {
-          const bool excl = (unsigned)(d0 + k - dstar + 1) <= 2u;
-          const uint32_t v = key[k] >> 16;
-          m2 = min(m2, excl ? 0xffffu : v);
-        }
-        m2 = __reduce_min_sync(FULL, m2);
-        uniq_ok = (int)m2 * k100u >= mval * 100;
-      } else {
-        bool ok = true;
-#pragma unroll
-        for (int k = 0; k < DPL; ++k) {
-          const int v = (int)(key[k] >> 16);
-          const int dd = d0 + k - dstar;
-          ok = ok && (!active || v * k100u >= mval * 100 || (dd >= -1 && dd <= 1));
-        }
-        uniq_ok = __all_sync(FULL, ok);
-      }
-      __syncwarp();
-      float disp = (float)dstar;
-      if (!uniq_ok) {
-        disp = -1.0f;
-      } else if (dstar != 0 && dstar != a.D - 1) {
-        const int y0 = my_la[dstar - 1], y2 = my_la[dstar + 1];
-        const float sub = (float)((1.0 * (double)(y2 - y0)) / (2.0 * (double)(y0 - 2 * mval + y2)));
-        disp = (float)dstar - sub;
-      }
-      __syncwarp();
-      if (lane == 0) a.dispL[rowpix + s] = disp;
-      // ---- right disparity: T_x(d) = min(T_{x-1}(d-1), key_x(d)) --------------------------
-      const uint32_t upT = __shfl_up_sync(FULL, T[DPL - 1], 1);
+      if (lane == 0) gkbuf[s & 31] = gk;
+      // ---- right disparity: T_x(d) = min(T_{x-1}(d-1), key_x(d))  (wta.cu:183,190-198) ---------
+      const uint32_t upT = __shfl_up_sync(FULL, T[DPL - 1], 1) | firstmask;
 #pragma unroll
       for (int k = DPL - 1; k >= 1; --k) T[k] = min(T[k - 1], key[k]);
-      T[0] = first_lane ? key[0] : min(upT, key[0]);
-      if (last_lane && s >= a.D - 1) a.dispR[rowpix + s - (a.D - 1)] = (uint16_t)(T[DPL - 1] & 0xffffu);
+      T[0] = min(upT, key[0]);
+      if (last_lane) rbuf[s & 31] = (uint16_t)T[DPL - 1]; // pixel s-(D-1), stored by the tile phase
     }
+  };
+
+  // one lane per pixel: uniqueness + sub-pixel for the (up to 32) pixels of the finished tile
+  auto tile_phase = [&](int t0, int cnt) {
+    __syncwarp();
+    if (lane < cnt) {
+      const uint32_t gk = gkbuf[lane];
+      const int m = (int)(gk >> 16), ds = (int)(gk & 0xffffu);
+      uint16_t *row = reinterpret_cast<uint16_t *>(tile + lane * TP);
+      int y0 = 0, y2 = 0;
+      if (ds > 0) y0 = row[ds - 1];
+      if (ds < D - 1) y2 = row[ds + 1];
+      bool ok;
+      if (k100u > 0) {
+        // unique <=> min over d outside [d*-1, d*+1] of LAll(d)*(100-u) >= m*100 (wta.cu:203)
+        if (ds > 0) row[ds - 1] = 0xffffu;
+        row[ds] = 0xffffu;
+        if (ds < D - 1) row[ds + 1] = 0xffffu;
+        uint32_t mn = 0xffffffffu;
+        const uint4 *r4 = reinterpret_cast<const uint4 *>(row);
+        for (int i = 0; i < D / 8; ++i) {
+          const uint4 v = r4[i];
+          mn = __vimin3_u16x2(mn, v.x, v.y);
+          mn = __vimin3_u16x2(mn, v.z, v.w);
+        }
+        const int m2 = (int)min(mn & 0xffffu, mn >> 16);
+        ok = m2 * k100u >= m * 100;
+      } else { // uniqueness_ratio >= 100: the product test is not monotone; evaluate it literally
+        ok = true;
+        for (int d = 0; d < D; ++d) {
+          const int dd = d - ds;
+          ok = ok && ((int)row[d] * k100u >= m * 100 || (dd >= -1 && dd <= 1));
+        }
+      }
+      float disp = (float)ds;
+      if (!ok) {
+        disp = -1.0f;
+      } else if (ds != 0 && ds != D - 1) {
+        // wta.cu:164-168 computes (double)(y2-y0) / (2.0*(double)(y0-2*y1+y2)) and rounds to float.
+        // Numerator and denominator are integers < 2^20, so ONE correctly rounded float division
+        // gives the same bits (no double-rounding case exists for |num|,den < 2^24).
+        disp = (float)ds - __fdiv_rn((float)(y2 - y0), (float)(2 * (y0 - 2 * m + y2)));
+      }
+      a.dispL[rowpix + t0 + lane] = disp;
+      const int xr = t0 + lane - (D - 1);
+      if (xr >= 0) a.dispR[rowpix + xr] = rbuf[lane];
+    }
+    __syncwarp();
+  };
+
+  int slot = 0;
+  uint32_t parity = 0;
+  for (int ci = 0; ci < nchunks; ++ci) {
+    mbar_wait(bar0 + 8 * slot, parity);
+    if (ci + NCH - 1 < nchunks) issue(ci + NCH - 1); // refills the slot consumed one chunk ago
+    const int s0 = ci * K;
+    const int kc = min(K, steps - s0);
+    const unsigned char *pc = ring + slot * K * PIECE + loff;
+    if (kc == K) {
+      if (hrev) {
+        pc += (K - 1) * PIECE;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { step(s0 + k, pc); pc -= PIECE; }
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) { step(s0 + k, pc); pc += PIECE; }
+      }
+    } else {
+      const int dp = hrev ? -PIECE : PIECE;
+      if (hrev) pc += (kc - 1) * PIECE;
+      for (int k = 0; k < kc; ++k) { step(s0 + k, pc); pc += dp; }
+    }
+    if (MODE == 2) {
+      const int done = s0 + kc;
+      if ((done & 31) == 0 || done == steps) tile_phase((done - 1) & ~31, done - ((done - 1) & ~31));
+    }
+    if (++slot == NCH) { slot = 0; parity ^= 1; }
   }
-  cp_async_wait<0>();
-  if (WTA && active) {
+  if (MODE == 2 && active) {
     // pixels whose diagonal leaves the image on the right: x' = cols-1-d, d < D-1
 #pragma unroll
     for (int k = 0; k < DPL; ++k) {
-      const int d = d0 + k;
+      const int d = lane * DPL + k;
       const int xp = a.cols - 1 - d;
-      if (d < a.D - 1 && xp >= 0) a.dispR[rowpix + xp] = (uint16_t)(T[k] & 0xffffu);
+      if (d < D - 1 && xp >= 0) a.dispR[rowpix + xp] = (uint16_t)(T[k] & 0xffffu);
     }
   }
 }
 
-constexpr int pf_for(int NR, int NAUX) {
-  // prefetch distance in path steps; the ring costs (1+NAUX)*(PF+1)*128*NR bytes per warp
-  int v = 96 / (NR * (1 + NAUX));
-  return v > 32 ? 32 : (v < 3 ? 3 : v);
-}
-
-template <int NR, int NAUX, bool WTA>
+template <int NR, int MODE, bool PARTIAL>
 static cudaError_t launch_one(const AggrArgs &a, int wpb, cudaStream_t st) {
-  constexpr int PF = pf_for(NR, NAUX);
+  constexpr int K0 = NR <= 16 ? (32 / NR < 2 ? 2 : 32 / NR) : 2;
+  constexpr int K = MODE == 1 ? (K0 >= 4 ? K0 / 2 : K0) : K0;
+  constexpr int NCH = MODE == 0 ? 4 : 3;
   const long npaths = (long)a.N * (a.vertical ? a.cols : a.rows);
   const unsigned blocks = (unsigned)((npaths + wpb - 1) / wpb);
-  const size_t smem = (size_t)wpb * ring_bytes_per_warp<NR, NAUX, PF>() + (WTA ? (size_t)wpb * a.D * sizeof(uint16_t) : 0);
-  auto k = aggr_kernel<NR, NAUX, WTA, PF>;
+  const size_t smem = (size_t)wpb * aggr_smem<MODE, K, NCH>(a.D).total;
+  auto k = aggr_kernel<NR, MODE, PARTIAL, K, NCH>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -299,21 +408,24 @@ static cudaError_t launch_one(const AggrArgs &a, int wpb, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-template <int NAUX, bool WTA>
-static cudaError_t dispatch(const AggrArgs &a, int wpb, cudaStream_t st) {
-  const int D = a.D;
-  if (D <= 64) return launch_one<1, NAUX, WTA>(a, wpb, st);
-  if (D <= 128) return launch_one<2, NAUX, WTA>(a, wpb, st);
-  if (D <= 256) return launch_one<4, NAUX, WTA>(a, wpb, st);
-  if (D <= 512) return launch_one<8, NAUX, WTA>(a, wpb, st);
-  return launch_one<16, NAUX, WTA>(a, wpb, st);
+static int nr_for(int D) { return D <= 64 ? 1 : D <= 128 ? 2 : D <= 256 ? 4 : D <= 512 ? 8 : 16; }
+
+template <int MODE> static cudaError_t dispatch(const AggrArgs &a, int wpb, cudaStream_t st) {
+  const int nr = nr_for(a.D);
+  const bool partial = a.D != 64 * nr;
+#define SSB_CASE(NRV)                                                                             \
+  case NRV: return partial ? launch_one<NRV, MODE, true>(a, wpb, st) : launch_one<NRV, MODE, false>(a, wpb, st);
+  switch (nr) {
+    SSB_CASE(1) SSB_CASE(2) SSB_CASE(4) SSB_CASE(8) SSB_CASE(16)
+  }
+#undef SSB_CASE
+  return cudaErrorInvalidValue;
 }
 
-static int dpl_for(int D) { return D <= 64 ? 2 : D <= 128 ? 4 : D <= 256 ? 8 : D <= 512 ? 16 : 32; }
-
 bool aggr_fast_supported(int D, int cmax, int P1, int P2) {
-  if (D < 2 || D > 1024) return false;
-  if (D % dpl_for(D) != 0) return false;
+  if (D < 8 || D > 1024) return false;
+  if (D % 8 != 0) return false;              // 16-byte bulk-copy granularity of one pixel's D u16 costs
+  if (D % (2 * nr_for(D)) != 0) return false; // whole lanes
   if (P1 < 0 || P2 < 0) return false;
   return 4L * ((long)cmax + P2) <= 65535L && (long)cmax + P2 + P1 <= 65535L;
 }
@@ -327,7 +439,6 @@ cudaError_t launch_aggr_wta(const AggrBuffers &b, int N, int rows, int cols, int
   a.N = N; a.rows = rows; a.cols = cols; a.D = D;
   a.P1P1 = (uint32_t)P1 * 0x10001u;
   a.P2P2 = (uint32_t)P2 * 0x10001u;
-  a.BIG = 0xffffu - (uint32_t)P1;
   a.uniq = uniq;
   cudaError_t err;
   // fork: right->left on the aux stream, top->bottom on the main stream
@@ -335,24 +446,24 @@ cudaError_t launch_aggr_wta(const AggrBuffers &b, int N, int rows, int cols, int
   if ((err = cudaStreamWaitEvent(s_aux, ev[0], 0)) != cudaSuccess) return err;
   AggrArgs h = a;
   h.vertical = 0; h.reverse = 1; h.out = b.L1;
-  if ((err = dispatch<0, false>(h, 2, s_aux)) != cudaSuccess) return err;
+  if ((err = dispatch<0>(h, 1, s_aux)) != cudaSuccess) return err;
   if ((err = cudaEventRecord(ev[1], s_aux)) != cudaSuccess) return err;
   AggrArgs v = a;
   v.vertical = 1; v.reverse = 0; v.out = b.L2;
-  if ((err = dispatch<0, false>(v, 8, stream)) != cudaSuccess) return err;
+  if ((err = dispatch<0>(v, 1, stream)) != cudaSuccess) return err;
   mark("aggr_down");
   if ((err = cudaStreamWaitEvent(stream, ev[1], 0)) != cudaSuccess) return err;
   mark("aggr_left_tail"); // time the right->left pass (aux stream) outlives the top->bottom one
   // bottom->top, accumulating L1+L2+L3
   AggrArgs u = a;
   u.vertical = 1; u.reverse = 1; u.aux0 = b.L1; u.aux1 = b.L2; u.out = b.S3; u.dbg0 = b.dbgL3;
-  if ((err = dispatch<2, false>(u, 8, stream)) != cudaSuccess) return err;
+  if ((err = dispatch<1>(u, 1, stream)) != cudaSuccess) return err;
   mark("aggr_up");
   // left->right + blend + winner-takes-all
   AggrArgs w = a;
   w.vertical = 0; w.reverse = 0; w.aux0 = b.S3; w.dbg0 = b.dbgL0; w.dbg1 = b.dbgLAll;
   w.dispL = b.dispL; w.dispR = b.dispR;
-  err = dispatch<1, true>(w, 2, stream);
+  err = dispatch<2>(w, 1, stream);
   mark("aggr_right_wta");
   return err;
 }
