@@ -10,57 +10,63 @@
 //
 // Mapping: a thread owns a disparity PAIR (packed u16x2) for a strip of TX output columns and
 // marches down a band of rows.  Per input row it computes TX+BW-1 Hamming pairs from census codes
-// staged in shared memory (1 LDS + 2 POPC per column), a sliding BW-wide horizontal sum in
-// registers, and a BH-deep vertical running sum whose leaving row comes from a thread-private
-// shared-memory ring.  ~ (TX+BW-1)/TX * (RY+BH-1)/RY POPC per output instead of BW*BH; stores are
-// 4 B per lane, 128 B per warp, and every volume byte is written exactly once.
+// staged in shared memory (vector LDS: 1/2 load for the right codes and 1/4 broadcast load for
+// the left code per column, 2 POPC), a sliding BW-wide horizontal sum in registers, and a BH-deep
+// vertical running sum whose leaving row comes from a thread-private shared-memory ring.
+// (TX+BW-1)/TX * (RY+BH-1)/RY POPC per output instead of BW*BH; the hot loop has no bounds
+// predicates (borders are resolved when the codes are staged; only the right-most column block
+// runs the EDGE variant), the next row's codes are fetched into registers while the current row is
+// processed, stores are 4 B per lane / 128 B per warp and every volume byte is written once.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace ssb {
 
-constexpr int COST_RY = 48; // output rows per band
-
-template <int BW, int BH, int TX, int NS, int TD>
-__global__ void __launch_bounds__(TD *NS)
-cost_kernel(const uint32_t *__restrict__ cL, const uint32_t *__restrict__ cR,
-            uint16_t *__restrict__ C, int rows, int cols, int D, int nchunks) {
+template <int BW, int BH, int TX, int NS, int TD, bool EDGE>
+__device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, const uint32_t *__restrict__ imR,
+                                          uint16_t *__restrict__ outC, int rows, int cols, int D, int dbase,
+                                          int xblk, int y_begin, int y_end, uint32_t *ring,
+                                          uint32_t *sLb, uint32_t *sRb) {
   constexpr int HW = BW / 2, HH = BH / 2;
   constexpr int NH = TX + BW - 1;       // hamming columns per strip
   constexpr int NXW = NS * TX + BW - 1; // left census codes staged per block
   constexpr int DC = 2 * TD;            // disparities per chunk
-  constexpr int NRC = NXW + DC;         // right census codes staged per block
+  constexpr int NRC = NXW + DC + 1;     // right census codes staged per block
   constexpr int SLOT = NS * TX * TD;    // ring words per input row
-  __shared__ uint32_t sL[2][NXW];
-  __shared__ uint32_t sR[2][NRC];
-  extern __shared__ uint32_t ring[]; // [BH][NS][TX][TD], thread-private entries
+  constexpr int nthreads = TD * NS;
+  constexpr int NLD = (NRC + nthreads - 1) / nthreads;
+  constexpr int SLS = (NXW + 3) & ~3, SRS = (NRC + 3) & ~3; // row strides keep vector loads aligned
 
   const int td = threadIdx.x; // disparity pair inside the chunk
   const int strip = threadIdx.y;
   const int tid = strip * TD + td;
-  constexpr int nthreads = TD * NS;
-  const int chunk = blockIdx.x % nchunks;
-  const int xblk = blockIdx.x / nchunks;
-  const int n = blockIdx.z;
-  const int dbase = chunk * DC;
-  const int d_lo = dbase + 2 * td;       // my disparities: d_lo, d_lo+1
-  const int xs = xblk * (NS * TX) - HW;  // image column of staged index 0
-  const int y_begin = blockIdx.y * COST_RY;
-  const int y_end = min(rows, y_begin + COST_RY);
-  const uint32_t *imL = cL + (size_t)n * rows * cols;
-  const uint32_t *imR = cR + (size_t)n * rows * cols;
-  uint16_t *outC = C + (size_t)n * rows * cols * D;
-  const int imax = cols - 1 - xs; // staged index of the last image column (replicate border)
+  const int d_lo = dbase + 2 * td;      // my disparities: d_lo, d_lo+1
+  const int xs = xblk * (NS * TX) - HW; // image column of staged index 0
+  const int imax = cols - 1 - xs;       // staged index of the last image column (replicate border)
+  const bool live = d_lo < D;
   const bool even_d = (D & 1) == 0;
 
-  auto stage = [&](int buf, int yin) {
+  // column indices this thread stages (row-independent).  sL[i] = cL(clamp(xs+i));
+  // sR[j] = cR(clamp(xs + j - DC - 1 - dbase)): column i, local disparity dl -> j = i - dl + DC + 1
+  const int colL = min(max(xs + tid, 0), cols - 1);
+  int colR[NLD];
+#pragma unroll
+  for (int k = 0; k < NLD; ++k) colR[k] = min(max(xs + tid + k * nthreads - DC - 1 - dbase, 0), cols - 1);
+  uint32_t vL = 0, vR[NLD];
+  auto gload = [&](int yin) {
     const int yc = min(max(yin, 0), rows - 1);
     const uint32_t *l = imL + (size_t)yc * cols;
     const uint32_t *r = imR + (size_t)yc * cols;
-    for (int i = tid; i < NXW; i += nthreads) sL[buf][i] = __ldg(l + min(max(xs + i, 0), cols - 1));
-    // sR[j] holds cR(y, max(xs + j - (DC-1) - dbase, 0)); column i / local disparity dl -> j = i-dl+DC-1
-    for (int j = tid; j < NRC; j += nthreads)
-      sR[buf][j] = __ldg(r + min(max(xs + j - (DC - 1) - dbase, 0), cols - 1));
+    if (tid < NXW) vL = __ldg(l + colL);
+#pragma unroll
+    for (int k = 0; k < NLD; ++k)
+      if (tid + k * nthreads < NRC) vR[k] = __ldg(r + colR[k]);
+  };
+  auto sstore = [&](int buf) {
+    if (tid < NXW) sLb[buf * SLS + tid] = vL;
+#pragma unroll
+    for (int k = 0; k < NLD; ++k)
+      if (tid + k * nthreads < NRC) sRb[buf * SRS + tid + k * nthreads] = vR[k];
   };
 
   uint32_t vacc[TX];
@@ -68,61 +74,107 @@ cost_kernel(const uint32_t *__restrict__ cL, const uint32_t *__restrict__ cR,
   for (int x = 0; x < TX; ++x) vacc[x] = 0;
   uint32_t *myring = ring + (size_t)strip * TX * TD + td;
   const int ib = strip * TX; // staged index of my first hamming column
+  // output cursor: element (y, xs+HW+ib, d_lo) of the first emitted row
+  const int xo0 = xs + HW + ib;
+  uint16_t *prow = outC + ((size_t)y_begin * cols + xo0) * D + d_lo;
+  const size_t rowpitch = (size_t)cols * D;
 
-  // input rows y_begin-HH .. y_end-1+HH (clamped); output row y is complete after input y+HH
   const int nin = (y_end - y_begin) + BH - 1;
-  stage(0, y_begin - HH);
+  gload(y_begin - HH);
+  sstore(0);
   __syncthreads();
+  int wslot = 0; // ring slot written by this input row; the oldest row lives in slot wslot+1 (mod BH)
   for (int it = 0; it < nin; ++it) {
     const int buf = it & 1;
-    if (it + 1 < nin) stage(buf ^ 1, y_begin - HH + it + 1);
-    // ---- Hamming pairs of my strip ---------------------------------------------------------
-    const uint32_t *pl = sL[buf];
-    const uint32_t *pr = sR[buf] + (DC - 1) - 2 * td;
-    uint32_t h[NH];
-    {
-      uint32_t r0 = pr[ib - 1], hcur = 0;
+    if (it + 1 < nin) gload(y_begin - HH + it + 1);
+    if (live) {
+      // ---- Hamming pairs of my strip ---------------------------------------------------------
+      const uint32_t *pl = sLb + buf * SLS + ib;                     // 16-byte aligned (ib % 16 == 0)
+      const uint32_t *pr = sRb + buf * SRS + (DC + 1 - 2 * td) + ib; // pr[i] = cR(x_i - d_lo); pr-1 is 8-byte aligned
+      uint32_t av[(NH + 3) & ~3], rv[(NH + 2) & ~1]; // rv[k] = pr[k-1]
+#pragma unroll
+      for (int i4 = 0; i4 < NH; i4 += 4) {
+        const uint4 a4 = *reinterpret_cast<const uint4 *>(pl + i4);
+        av[i4] = a4.x; av[i4 + 1] = a4.y; av[i4 + 2] = a4.z; av[i4 + 3] = a4.w;
+      }
+#pragma unroll
+      for (int k = 0; k < NH + 1; k += 2) {
+        const uint2 r2 = *reinterpret_cast<const uint2 *>(pr - 1 + k);
+        rv[k] = r2.x; rv[k + 1] = r2.y;
+      }
+      uint32_t h[NH];
+      uint32_t hcur = 0;
 #pragma unroll
       for (int i = 0; i < NH; ++i) {
-        if (ib + i <= imax) {
-          const uint32_t r1 = r0; // code for d_lo+1 at this column == code for d_lo one column left
-          r0 = pr[ib + i];
-          const uint32_t a = pl[ib + i];
-          hcur = (uint32_t)__popc(a ^ r0) | ((uint32_t)__popc(a ^ r1) << 16);
-        }
-        h[i] = hcur;
+        // code for d_lo+1 at this column == code for d_lo one column to the left
+        const uint32_t hv = (uint32_t)__popc(av[i] ^ rv[i + 1]) + ((uint32_t)__popc(av[i] ^ rv[i]) << 16);
+        if (EDGE) { if (ib + i <= imax) hcur = hv; h[i] = hcur; }
+        else h[i] = hv;
       }
-    }
-    // ---- sliding BW-sum along x, BH-deep running sum along y -------------------------------
-    uint32_t *rs_w = myring + (size_t)(it % BH) * SLOT;
-    const uint32_t *rs_r = myring + (size_t)((it + 1) % BH) * SLOT;
-    const int y = y_begin + it - (BH - 1);
-    const bool emit = it >= BH - 1;
-    uint32_t hs = 0;
+      // ---- sliding BW-sum along x, BH-deep running sum along y -------------------------------
+      uint32_t *rs_w = myring + (size_t)wslot * SLOT;
+      const int rslot = wslot + 1 == BH ? 0 : wslot + 1;
+      const uint32_t *rs_r = myring + (size_t)rslot * SLOT;
+      uint32_t hs = 0;
 #pragma unroll
-    for (int i = 0; i < BW - 1; ++i) hs += h[i];
+      for (int i = 0; i < BW - 1; ++i) hs += h[i];
+      if (it < BH - 1) {
 #pragma unroll
-    for (int x = 0; x < TX; ++x) {
-      hs += h[x + BW - 1];
-      vacc[x] += hs;
-      rs_w[x * TD] = hs;
-      hs -= h[x];
-      if (emit) {
-        const int xo = xs + HW + ib + x;
-        if (xo < cols && d_lo < D) {
-          uint16_t *dst = outC + ((size_t)y * cols + xo) * D + d_lo;
-          if (even_d) {
-            *reinterpret_cast<uint32_t *>(dst) = vacc[x];
-          } else {
-            dst[0] = (uint16_t)(vacc[x] & 0xffffu);
-            if (d_lo + 1 < D) dst[1] = (uint16_t)(vacc[x] >> 16);
+        for (int x = 0; x < TX; ++x) {
+          hs += h[x + BW - 1];
+          vacc[x] += hs;
+          rs_w[x * TD] = hs;
+          hs -= h[x];
+        }
+      } else {
+        uint16_t *dst = prow;
+#pragma unroll
+        for (int x = 0; x < TX; ++x) {
+          hs += h[x + BW - 1];
+          vacc[x] += hs;
+          rs_w[x * TD] = hs;
+          hs -= h[x];
+          if (!EDGE || xo0 + x < cols) {
+            if (even_d) {
+              *reinterpret_cast<uint32_t *>(dst) = vacc[x];
+            } else {
+              dst[0] = (uint16_t)(vacc[x] & 0xffffu);
+              if (d_lo + 1 < D) dst[1] = (uint16_t)(vacc[x] >> 16);
+            }
           }
+          dst += D;
+          vacc[x] -= rs_r[x * TD]; // the row that leaves the window before the next input
         }
-        vacc[x] -= rs_r[x * TD]; // the row that leaves the window before the next input
+        prow += rowpitch;
       }
     }
+    wslot = wslot + 1 == BH ? 0 : wslot + 1;
+    if (it + 1 < nin) sstore(buf ^ 1);
     __syncthreads();
   }
+}
+
+template <int BW, int BH, int TX, int NS, int TD>
+__global__ void __launch_bounds__(TD *NS)
+cost_kernel(const uint32_t *__restrict__ cL, const uint32_t *__restrict__ cR,
+            uint16_t *__restrict__ C, int rows, int cols, int D, int nchunks, int ry) {
+  constexpr int NXW = NS * TX + BW - 1;
+  __shared__ __align__(16) uint32_t sL[2 * ((NXW + 3) & ~3)];
+  __shared__ __align__(16) uint32_t sR[2 * ((NXW + 2 * TD + 1 + 3) & ~3) + 4];
+  extern __shared__ uint32_t ring[]; // [BH][NS][TX][TD], thread-private entries
+  const int chunk = blockIdx.x % nchunks;
+  const int xblk = blockIdx.x / nchunks;
+  const int n = blockIdx.z;
+  const int y_begin = blockIdx.y * ry;
+  const int y_end = min(rows, y_begin + ry);
+  const uint32_t *imL = cL + (size_t)n * rows * cols;
+  const uint32_t *imR = cR + (size_t)n * rows * cols;
+  uint16_t *outC = C + (size_t)n * rows * cols * D;
+  const bool edge = (xblk + 1) * (NS * TX) + BW / 2 > cols; // needs the replicate-border hold / x bound
+  if (edge)
+    cost_band<BW, BH, TX, NS, TD, true>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR);
+  else
+    cost_band<BW, BH, TX, NS, TD, false>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR);
 }
 
 // Any block size: direct evaluation (bw*bh POPC per output).  Only used for block sizes that have
@@ -152,32 +204,44 @@ __global__ void cost_generic_kernel(const uint32_t *__restrict__ cL, const uint3
   C[idx] = (uint16_t)acc;
 }
 
+static int g_sm_count = 0;
+
+template <int BW, int BH, int TX, int NS, int TD>
+static cudaError_t launch_cfg(const uint32_t *cL, const uint32_t *cR, uint16_t *C, int N, int rows,
+                              int cols, int D, cudaStream_t st) {
+  auto k = cost_kernel<BW, BH, TX, NS, TD>;
+  const size_t smem = (size_t)BH * NS * TX * TD * sizeof(uint32_t);
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (g_sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, TD * NS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int nchunks = (D + 2 * TD - 1) / (2 * TD);
+  const long xb = (long)((cols + NS * TX - 1) / (NS * TX)) * nchunks;
+  // Row bands: as many as fit in ONE resident wave (no tail), at least 24 rows each so that the
+  // BH-1 warm-up rows stay a small overhead; big batches simply use 64-row bands.
+  const long capacity = (long)g_sm_count * per_sm;
+  long bands = capacity / (xb * N);
+  const long max_bands = (rows + 23) / 24, min_bands = (rows + 63) / 64;
+  if (bands > max_bands) bands = max_bands;
+  if (bands < min_bands) bands = min_bands;
+  const int ry = (int)((rows + bands - 1) / bands);
+  dim3 grid((unsigned)xb, (unsigned)((rows + ry - 1) / ry), (unsigned)N);
+  k<<<grid, dim3(TD, NS), smem, st>>>(cL, cR, C, rows, cols, D, nchunks, ry);
+  return cudaGetLastError();
+}
+
 template <int BW, int BH>
 static cudaError_t launch_fast(const uint32_t *cL, const uint32_t *cR, uint16_t *C, int N, int rows,
                                int cols, int D, cudaStream_t st) {
   constexpr int TX = 16;
-  if (D <= 64) {
-    constexpr int TD = 32, NS = 4;
-    auto k = cost_kernel<BW, BH, TX, NS, TD>;
-    const size_t smem = (size_t)BH * NS * TX * TD * sizeof(uint32_t);
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    const int nchunks = (D + 2 * TD - 1) / (2 * TD);
-    dim3 grid((unsigned)(((cols + NS * TX - 1) / (NS * TX)) * nchunks),
-              (unsigned)((rows + COST_RY - 1) / COST_RY), (unsigned)N);
-    k<<<grid, dim3(TD, NS), smem, st>>>(cL, cR, C, rows, cols, D, nchunks);
-  } else {
-    constexpr int TD = 64, NS = 2;
-    auto k = cost_kernel<BW, BH, TX, NS, TD>;
-    const size_t smem = (size_t)BH * NS * TX * TD * sizeof(uint32_t);
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    const int nchunks = (D + 2 * TD - 1) / (2 * TD);
-    dim3 grid((unsigned)(((cols + NS * TX - 1) / (NS * TX)) * nchunks),
-              (unsigned)((rows + COST_RY - 1) / COST_RY), (unsigned)N);
-    k<<<grid, dim3(TD, NS), smem, st>>>(cL, cR, C, rows, cols, D, nchunks);
-  }
-  return cudaGetLastError();
+  if (D <= 64) return launch_cfg<BW, BH, TX, 4, 32>(cL, cR, C, N, rows, cols, D, st);
+  return launch_cfg<BW, BH, TX, 2, 64>(cL, cR, C, N, rows, cols, D, st);
 }
 
 cudaError_t launch_cost(const uint32_t *cL, const uint32_t *cR, uint16_t *C, int N, int rows,
