@@ -127,73 +127,40 @@ __device__ __forceinline__ void sgm_step(uint32_t (&L)[NR], const uint32_t (&c)[
 }
 
 // MODE 0: plain path (out = L).  MODE 1: out = L + aux0 + aux1.  MODE 2: left->right path,
-// LAll = (L + aux0)/4, winner-takes-all (horizontal forward only).
+// LAll = (L + aux0)/4, winner-takes-all (horizontal forward only; producer + consumer warp).
 template <int MODE> __host__ __device__ constexpr int nstream() { return MODE == 0 ? 1 : (MODE == 1 ? 3 : 2); }
 
-struct AggrSmem { // per-warp layout (bytes); PIECE = D*2
+struct AggrSmem { // per-path layout (bytes); PIECE = D*2
   int ring, tile, gk, rb, total;
 };
+constexpr int WTA_TILES = 2; // LAll tiles (32 pixels each) between the SGM warp and the WTA warp
 template <int MODE, int K, int NCH> __host__ __device__ inline AggrSmem aggr_smem(int D) {
   AggrSmem s;
   const int piece = D * 2;
-  s.ring = 64; // NCH mbarriers first (NCH <= 8)
+  s.ring = 64; // mbarriers first: NCH bulk-copy barriers, then (MODE 2) WTA_TILES full + WTA_TILES empty
   s.tile = s.ring + nstream<MODE>() * NCH * K * piece;
-  s.gk = s.tile + (MODE == 2 ? 32 * (piece + 16) : 0);
+  s.gk = s.tile + (MODE == 2 ? WTA_TILES * 32 * (piece + 16) : 0);
   s.rb = s.gk + (MODE == 2 ? 32 * 4 : 0);
   s.total = s.rb + (MODE == 2 ? 32 * 2 : 0);
   s.total = (s.total + 127) & ~127;
   return s;
 }
 
-template <int NR, int MODE, bool PARTIAL, int K, int NCH>
-__global__ void __launch_bounds__(128) aggr_kernel(const AggrArgs a) {
-  constexpr int DPL = 2 * NR;
-  constexpr int NS = nstream<MODE>();
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int wpb = blockDim.x >> 5;
-  const long path = (long)blockIdx.x * wpb + warp;
-  const int per_env = a.vertical ? a.cols : a.rows;
-  if (path >= (long)a.N * per_env) return; // warps are independent: no block-level barrier anywhere
-  const int n = (int)(path / per_env);
-  const int q = (int)(path - (long)n * per_env);
-  const int steps = a.vertical ? a.rows : a.cols;
-  const int D = a.D;
-  const int PIECE = D * 2;
-  const AggrSmem lay = aggr_smem<MODE, K, NCH>(D);
-  unsigned char *wsm = smem_raw + (size_t)warp * lay.total;
-  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(wsm);
-  unsigned char *ring = wsm + lay.ring;
-  const uint32_t ring_s = bar0 + lay.ring;
-  const int STREAM = NCH * K * PIECE; // bytes per stream in the ring
-
-  // byte offset of path step 0, disparity 0, and the signed byte stride between steps
-  const size_t env = (size_t)n * a.rows * a.cols * D;
-  size_t e0 = env + (a.vertical ? (size_t)q * D : (size_t)q * a.cols * D);
-  long sstride = a.vertical ? (long)a.cols * D * 2 : (long)PIECE;
-  if (a.reverse) { e0 += (size_t)(steps - 1) * (size_t)(sstride / 2); sstride = -sstride; }
-  const char *gC = reinterpret_cast<const char *>(a.C + e0);
-  const char *gA0 = NS > 1 ? reinterpret_cast<const char *>(a.aux0 + e0) : nullptr;
-  const char *gA1 = NS > 2 ? reinterpret_cast<const char *>(a.aux1 + e0) : nullptr;
-
-  const int nact = D / DPL; // active lanes
-  const bool active = !PARTIAL || lane < nact;
-  const int loff = lane * NR * 4; // byte offset of this lane inside a piece
-  const uint32_t selUp = lane == 0 ? 0x5454u : 0x5432u;
-  const uint32_t selDn = lane == nact - 1 ? 0x3232u : 0x5432u;
-  const bool hrev = !a.vertical && a.reverse; // chunk lies in memory in descending step order
-
-  if (lane == 0) {
+// The bulk-copy ring of one path: NS streams x NCH chunk slots x K steps x PIECE bytes.
+template <int NS, int K, int NCH> struct PathRing {
+  uint32_t bar0, ring_s;
+  const char *g[3];
+  long sstride;
+  int steps, PIECE, STREAM, lane;
+  bool vertical, hrev;
+  __device__ __forceinline__ void init() const {
+    if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) mbar_init(bar0 + 8 * i, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      for (int i = 0; i < NCH; ++i) mbar_init(bar0 + 8 * i, 1);
+    }
   }
-  __syncwarp();
-
-  const int nchunks = (steps + K - 1) / K;
-  auto issue = [&](int ci) {
+  // all lanes call; chunk ci -> slot ci % NCH
+  __device__ __forceinline__ void issue(int ci) const {
     const int slot = ci % NCH;
     const int s0 = ci * K;
     const int kc = min(K, steps - s0);
@@ -201,116 +168,309 @@ __global__ void __launch_bounds__(128) aggr_kernel(const AggrArgs a) {
     if (lane == 0) mbar_expect_tx(bar, (uint32_t)(kc * PIECE * NS));
     __syncwarp();
     const uint32_t dst = ring_s + (uint32_t)(slot * K * PIECE);
-    if (a.vertical) {
+    if (vertical) {
       if (lane < kc) {
         const long off = (long)(s0 + lane) * sstride;
         const uint32_t d = dst + (uint32_t)(lane * PIECE);
-        bulk_g2s(d, gC + off, (uint32_t)PIECE, bar);
-        if (NS > 1) bulk_g2s(d + STREAM, gA0 + off, (uint32_t)PIECE, bar);
-        if (NS > 2) bulk_g2s(d + 2 * STREAM, gA1 + off, (uint32_t)PIECE, bar);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) bulk_g2s(d + i * STREAM, g[i] + off, (uint32_t)PIECE, bar);
       }
     } else if (lane == 0) {
       const long off = (long)(hrev ? s0 + kc - 1 : s0) * sstride;
       const uint32_t bytes = (uint32_t)(kc * PIECE);
-      bulk_g2s(dst, gC + off, bytes, bar);
-      if (NS > 1) bulk_g2s(dst + STREAM, gA0 + off, bytes, bar);
-      if (NS > 2) bulk_g2s(dst + 2 * STREAM, gA1 + off, bytes, bar);
+#pragma unroll
+      for (int i = 0; i < NS; ++i) bulk_g2s(dst + i * STREAM, g[i] + off, bytes, bar);
     }
-  };
-  for (int ci = 0; ci < NCH - 1 && ci < nchunks; ++ci) issue(ci);
+  }
+};
+
+struct PathGeom {
+  int n, q, steps;
+  size_t e0;    // element offset of path step 0, disparity 0
+  long sstride; // signed byte stride between steps
+};
+__device__ __forceinline__ PathGeom path_geom(const AggrArgs &a, long path) {
+  PathGeom g;
+  const int per_env = a.vertical ? a.cols : a.rows;
+  g.n = (int)(path / per_env);
+  g.q = (int)(path - (long)g.n * per_env);
+  g.steps = a.vertical ? a.rows : a.cols;
+  const size_t env = (size_t)g.n * a.rows * a.cols * a.D;
+  g.e0 = env + (a.vertical ? (size_t)g.q * a.D : (size_t)g.q * a.cols * a.D);
+  g.sstride = a.vertical ? (long)a.cols * a.D * 2 : (long)a.D * 2;
+  if (a.reverse) { g.e0 += (size_t)(g.steps - 1) * (size_t)(g.sstride / 2); g.sstride = -g.sstride; }
+  return g;
+}
+
+// ---- MODE 0 / 1: one independent warp per path ---------------------------------------------------
+template <int NR, int MODE, bool PARTIAL, bool DBG, int K, int NCH>
+__global__ void __launch_bounds__(128) aggr_kernel(const AggrArgs a) {
+  static_assert(MODE == 0 || MODE == 1, "plain passes only");
+  constexpr int DPL = 2 * NR;
+  constexpr int NS = nstream<MODE>();
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  const long path = (long)blockIdx.x * wpb + warp;
+  if (path >= (long)a.N * (a.vertical ? a.cols : a.rows)) return; // warps are independent: no block barrier
+  const PathGeom pg = path_geom(a, path);
+  const int steps = pg.steps;
+  const int D = a.D;
+  const int PIECE = D * 2;
+  const AggrSmem lay = aggr_smem<MODE, K, NCH>(D);
+  unsigned char *wsm = smem_raw + (size_t)warp * lay.total;
+  PathRing<NS, K, NCH> pr;
+  pr.bar0 = (uint32_t)__cvta_generic_to_shared(wsm);
+  pr.ring_s = pr.bar0 + lay.ring;
+  pr.g[0] = reinterpret_cast<const char *>(a.C + pg.e0);
+  pr.g[1] = NS > 1 ? reinterpret_cast<const char *>(a.aux0 + pg.e0) : nullptr;
+  pr.g[2] = NS > 2 ? reinterpret_cast<const char *>(a.aux1 + pg.e0) : nullptr;
+  pr.sstride = pg.sstride; pr.steps = steps; pr.PIECE = PIECE; pr.STREAM = NCH * K * PIECE; pr.lane = lane;
+  pr.vertical = a.vertical != 0; pr.hrev = !a.vertical && a.reverse;
+  const unsigned char *ring = wsm + lay.ring;
+  const int STREAM = pr.STREAM;
+  const bool hrev = pr.hrev;
+
+  const int nact = D / DPL; // active lanes
+  const bool active = !PARTIAL || lane < nact;
+  const int loff = lane * NR * 4; // byte offset of this lane inside a piece
+  const uint32_t selUp = lane == 0 ? 0x5454u : 0x5432u;
+  const uint32_t selDn = lane == nact - 1 ? 0x3232u : 0x5432u;
+
+  pr.init();
+  if (lane == 0) {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+  const int nchunks = (steps + K - 1) / K;
+  for (int ci = 0; ci < NCH - 1 && ci < nchunks; ++ci) pr.issue(ci);
 
   uint32_t L[NR];
 #pragma unroll
   for (int r = 0; r < NR; ++r) L[r] = active ? 0u : 0xffffffffu;
+  char *pOut = reinterpret_cast<char *>(a.out + pg.e0) + loff;
+  char *pDbg0 = DBG ? reinterpret_cast<char *>(a.dbg0 + pg.e0) + loff : nullptr;
+  const long sstride = pg.sstride;
 
-  // output cursors (bytes)
-  char *pOut = MODE != 2 ? reinterpret_cast<char *>(a.out + e0) + loff : nullptr;
-  char *pDbg0 = a.dbg0 ? reinterpret_cast<char *>(a.dbg0 + e0) + loff : nullptr;
-  char *pDbg1 = (MODE == 2 && a.dbg1) ? reinterpret_cast<char *>(a.dbg1 + e0) + loff : nullptr;
-
-  // ---- winner-takes-all state (MODE 2) ----------------------------------------------------------
-  uint32_t T[DPL], dconst[NR];
-#pragma unroll
-  for (int k = 0; k < DPL; ++k) T[k] = 0xffffffffu;
-#pragma unroll
-  for (int r = 0; r < NR; ++r) dconst[r] = (uint32_t)(lane * DPL + 2 * r) | ((uint32_t)(lane * DPL + 2 * r + 1) << 16);
-  const int TP = PIECE + 16; // tile row pitch: lanes of the per-pixel phase hit distinct banks
-  unsigned char *tile = wsm + lay.tile;
-  uint32_t *gkbuf = reinterpret_cast<uint32_t *>(wsm + lay.gk);
-  uint16_t *rbuf = reinterpret_cast<uint16_t *>(wsm + lay.rb);
-  const size_t rowpix = MODE == 2 ? ((size_t)n * a.rows + q) * a.cols : 0;
-  const int k100u = 100 - a.uniq;
-  const uint32_t firstmask = lane == 0 ? 0xffffffffu : 0u;
-  const bool last_lane = lane == nact - 1;
-
-  auto step = [&](int s, const unsigned char *pc) {
+  auto step = [&](const unsigned char *pc) {
     uint32_t c[NR], x0[NR], x1[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) { c[r] = 0; x0[r] = 0; x1[r] = 0; }
     if (active) {
       lds_vec<NR>(pc, c);
       if (NS > 1) lds_vec<NR>(pc + STREAM, x0);
       if (NS > 2) lds_vec<NR>(pc + 2 * STREAM, x1);
-    } else {
-#pragma unroll
-      for (int r = 0; r < NR; ++r) { c[r] = 0; x0[r] = 0; x1[r] = 0; }
     }
     sgm_step<NR>(L, c, a.P1P1, a.P2P2, selUp, selDn);
     if (PARTIAL) {
 #pragma unroll
       for (int r = 0; r < NR; ++r) L[r] = active ? L[r] : 0xffffffffu;
     }
-    if (MODE != 2) {
-      if (active) {
-        if (MODE == 0) {
-          st_vec<NR>(pOut, L);
-        } else {
-          uint32_t o[NR];
+    if (active) {
+      if (MODE == 0) {
+        st_vec<NR>(pOut, L);
+      } else {
+        uint32_t o[NR];
 #pragma unroll
-          for (int r = 0; r < NR; ++r) o[r] = L[r] + x0[r] + x1[r];
-          st_vec<NR>(pOut, o);
-          if (pDbg0) { st_vec<NR>(pDbg0, L); }
-        }
+        for (int r = 0; r < NR; ++r) o[r] = L[r] + x0[r] + x1[r];
+        st_vec<NR>(pOut, o);
+        if (DBG) st_vec<NR>(pDbg0, L);
       }
-      pOut += sstride;
-      if (MODE == 1 && pDbg0) pDbg0 += sstride;
+    }
+    pOut += sstride;
+    if (DBG) pDbg0 += sstride;
+  };
+
+  int slot = 0;
+  uint32_t parity = 0;
+  for (int ci = 0; ci < nchunks; ++ci) {
+    mbar_wait(pr.bar0 + 8 * slot, parity);
+    if (ci + NCH - 1 < nchunks) pr.issue(ci + NCH - 1); // refills the slot consumed one chunk ago
+    const int kc = min(K, steps - ci * K);
+    const unsigned char *pc = ring + slot * K * PIECE + loff;
+    if (kc == K) {
+      if (hrev) {
+        pc += (K - 1) * PIECE;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { step(pc); pc -= PIECE; }
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) { step(pc); pc += PIECE; }
+      }
     } else {
-      // ---- blend: LAll = (L0 + (L1+L2+L3)) / 4 per 16-bit half (aggr.cu:192,222) ---------------
+      const int dp = hrev ? -PIECE : PIECE;
+      if (hrev) pc += (kc - 1) * PIECE;
+      for (int k = 0; k < kc; ++k) { step(pc); pc += dp; }
+    }
+    if (++slot == NCH) { slot = 0; parity ^= 1; }
+  }
+}
+
+// ---- MODE 2: left->right path + blend + winner-takes-all, two warps per image row ---------------
+// Warp 0 (producer) walks the path: SGM step, LAll = (L0 + S3)/4, row -> shared tile.  Warp 1
+// (consumer) follows one tile (32 pixels) behind: packed (min,argmin) keys, the right-disparity
+// diagonal recurrence, and after each tile the one-lane-per-pixel uniqueness / sub-pixel phase.
+// Hand-over through two full/empty mbarrier pairs, so the serial SGM chain never waits for the
+// winner-takes-all arithmetic.
+template <int NR, bool PARTIAL, bool DBG, int K, int NCH>
+__global__ void __launch_bounds__(128) aggr_wta_kernel(const AggrArgs a) {
+  constexpr int DPL = 2 * NR;
+  constexpr int NS = 2;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int role = warp & 1;
+  const int ppb = blockDim.x >> 6; // paths (rows) per block
+  const long path = (long)blockIdx.x * ppb + (warp >> 1);
+  const bool valid = path < (long)a.N * a.rows;
+  const int D = a.D;
+  const int PIECE = D * 2;
+  const AggrSmem lay = aggr_smem<2, K, NCH>(D);
+  unsigned char *wsm = smem_raw + (size_t)(warp >> 1) * lay.total;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(wsm);
+  const uint32_t barFull = bar0 + 8 * NCH, barEmpty = barFull + 8 * WTA_TILES;
+  if (role == 0 && lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NCH + 2 * WTA_TILES; ++i) mbar_init(bar0 + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads(); // the only block-level barrier: mbarriers are initialised
+  if (!valid) return;
+  const PathGeom pg = path_geom(a, path);
+  const int steps = pg.steps; // == cols
+  const int nact = D / DPL;
+  const bool active = !PARTIAL || lane < nact;
+  const int loff = lane * NR * 4;
+  const int TP = PIECE + 16; // tile row pitch: the per-pixel phase's lanes hit distinct banks
+  unsigned char *tile = wsm + lay.tile;
+  const int ntiles = (steps + 31) / 32;
+
+  if (role == 0) {
+    // =========================== producer: SGM path + blend ===================================
+    PathRing<NS, K, NCH> pr;
+    pr.bar0 = bar0;
+    pr.ring_s = bar0 + lay.ring;
+    pr.g[0] = reinterpret_cast<const char *>(a.C + pg.e0);
+    pr.g[1] = reinterpret_cast<const char *>(a.aux0 + pg.e0);
+    pr.g[2] = nullptr;
+    pr.sstride = pg.sstride; pr.steps = steps; pr.PIECE = PIECE; pr.STREAM = NCH * K * PIECE; pr.lane = lane;
+    pr.vertical = false; pr.hrev = false;
+    const unsigned char *ring = wsm + lay.ring;
+    const int STREAM = pr.STREAM;
+    const uint32_t selUp = lane == 0 ? 0x5454u : 0x5432u;
+    const uint32_t selDn = lane == nact - 1 ? 0x3232u : 0x5432u;
+    const int nchunks = (steps + K - 1) / K;
+    for (int ci = 0; ci < NCH - 1 && ci < nchunks; ++ci) pr.issue(ci);
+    uint32_t L[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) L[r] = active ? 0u : 0xffffffffu;
+    char *pDbg0 = DBG ? reinterpret_cast<char *>(a.dbg0 + pg.e0) + loff : nullptr;
+    char *pDbg1 = DBG ? reinterpret_cast<char *>(a.dbg1 + pg.e0) + loff : nullptr;
+
+    auto step = [&](const unsigned char *pc, unsigned char *trow) {
+      uint32_t c[NR], x0[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) { c[r] = 0; x0[r] = 0; }
+      if (active) {
+        lds_vec<NR>(pc, c);
+        lds_vec<NR>(pc + STREAM, x0);
+      }
+      sgm_step<NR>(L, c, a.P1P1, a.P2P2, selUp, selDn);
+      if (PARTIAL) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) L[r] = active ? L[r] : 0xffffffffu;
+      }
+      // blend: LAll = (L0 + (L1+L2+L3)) / 4 per 16-bit half (aggr.cu:192,222)
       uint32_t la[NR];
 #pragma unroll
       for (int r = 0; r < NR; ++r) la[r] = ((L[r] + x0[r]) >> 2) & 0x3fff3fffu;
-      unsigned char *trow = tile + (s & 31) * TP;
       if (active) {
-        st_vec<NR>(trow + loff, la);
-        if (pDbg0) { st_vec<NR>(pDbg0, L); st_vec<NR>(pDbg1, la); }
+        st_vec<NR>(trow, la);
+        if (DBG) { st_vec<NR>(pDbg0, L); st_vec<NR>(pDbg1, la); }
       }
-      if (pDbg0) { pDbg0 += sstride; pDbg1 += sstride; }
-      // ---- keys (value << 16 | d): u32 min == lowest value, then lowest d (wta.cu:30-65) -------
-      uint32_t key[DPL];
-#pragma unroll
-      for (int r = 0; r < NR; ++r) {
-        key[2 * r] = active ? __byte_perm(la[r], dconst[r], 0x1054) : 0xffffffffu;
-        key[2 * r + 1] = active ? __byte_perm(la[r], dconst[r], 0x3276) : 0xffffffffu;
+      if (DBG) { pDbg0 += PIECE; pDbg1 += PIECE; }
+    };
+
+    int slot = 0;
+    uint32_t parity = 0;
+    for (int ci = 0; ci < nchunks; ++ci) {
+      const int s0 = ci * K;
+      if ((s0 & 31) == 0) { // entering tile t: the consumer must have released it (tile t - WTA_TILES)
+        const int t = s0 >> 5;
+        if (t >= WTA_TILES) mbar_wait(barEmpty + 8 * (t % WTA_TILES), (uint32_t)((t / WTA_TILES - 1) & 1));
       }
-      uint32_t lk = key[0];
+      mbar_wait(bar0 + 8 * slot, parity);
+      if (ci + NCH - 1 < nchunks) pr.issue(ci + NCH - 1);
+      const int kc = min(K, steps - s0);
+      const unsigned char *pc = ring + slot * K * PIECE + loff;
+      unsigned char *trow = tile + (s0 % (32 * WTA_TILES)) * TP + loff;
+      if (kc == K) {
 #pragma unroll
-      for (int k = 1; k < DPL; ++k) lk = min(lk, key[k]);
-      const uint32_t gk = __reduce_min_sync(FULL, lk);
-      if (lane == 0) gkbuf[s & 31] = gk;
-      // ---- right disparity: T_x(d) = min(T_{x-1}(d-1), key_x(d))  (wta.cu:183,190-198) ---------
-      const uint32_t upT = __shfl_up_sync(FULL, T[DPL - 1], 1) | firstmask;
-#pragma unroll
-      for (int k = DPL - 1; k >= 1; --k) T[k] = min(T[k - 1], key[k]);
-      T[0] = min(upT, key[0]);
-      if (last_lane) rbuf[s & 31] = (uint16_t)T[DPL - 1]; // pixel s-(D-1), stored by the tile phase
+        for (int k = 0; k < K; ++k) { step(pc, trow); pc += PIECE; trow += TP; }
+      } else {
+        for (int k = 0; k < kc; ++k) { step(pc, trow); pc += PIECE; trow += TP; }
+      }
+      const int done = s0 + kc;
+      if ((done & 31) == 0 || done == steps) { // tile complete: publish it
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t bar = barFull + 8 * (((done - 1) >> 5) % WTA_TILES);
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+        }
+      }
+      if (++slot == NCH) { slot = 0; parity ^= 1; }
     }
+    return;
+  }
+
+  // ============================== consumer: winner-takes-all ===================================
+  uint32_t T[DPL], dconst[NR];
+#pragma unroll
+  for (int k = 0; k < DPL; ++k) T[k] = 0xffffffffu;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) dconst[r] = (uint32_t)(lane * DPL + 2 * r) | ((uint32_t)(lane * DPL + 2 * r + 1) << 16);
+  uint32_t *gkbuf = reinterpret_cast<uint32_t *>(wsm + lay.gk);
+  uint16_t *rbuf = reinterpret_cast<uint16_t *>(wsm + lay.rb);
+  const size_t rowpix = ((size_t)pg.n * a.rows + pg.q) * a.cols;
+  const int k100u = 100 - a.uniq;
+  const uint32_t firstmask = lane == 0 ? 0xffffffffu : 0u;
+  const bool last_lane = lane == nact - 1;
+
+  auto cstep = [&](const unsigned char *trow, int k) {
+    uint32_t la[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) la[r] = 0;
+    if (active) lds_vec<NR>(trow, la);
+    // keys (value << 16 | d): u32 min == lowest value, then lowest d (wta.cu:30-65)
+    uint32_t key[DPL];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      key[2 * r] = active ? __byte_perm(la[r], dconst[r], 0x1054) : 0xffffffffu;
+      key[2 * r + 1] = active ? __byte_perm(la[r], dconst[r], 0x3276) : 0xffffffffu;
+    }
+    uint32_t lk = key[0];
+#pragma unroll
+    for (int j = 1; j < DPL; ++j) lk = min(lk, key[j]);
+    const uint32_t gk = __reduce_min_sync(FULL, lk);
+    if (lane == 0) gkbuf[k] = gk;
+    // right disparity: T_x(d) = min(T_{x-1}(d-1), key_x(d))  (wta.cu:183,190-198)
+    const uint32_t upT = __shfl_up_sync(FULL, T[DPL - 1], 1) | firstmask;
+#pragma unroll
+    for (int j = DPL - 1; j >= 1; --j) T[j] = min(T[j - 1], key[j]);
+    T[0] = min(upT, key[0]);
+    if (last_lane) rbuf[k] = (uint16_t)T[DPL - 1]; // pixel s-(D-1), stored by the tile phase
   };
 
   // one lane per pixel: uniqueness + sub-pixel for the (up to 32) pixels of the finished tile
-  auto tile_phase = [&](int t0, int cnt) {
+  auto tile_phase = [&](unsigned char *tbase, int t0, int cnt) {
     __syncwarp();
     if (lane < cnt) {
       const uint32_t gk = gkbuf[lane];
       const int m = (int)(gk >> 16), ds = (int)(gk & 0xffffu);
-      uint16_t *row = reinterpret_cast<uint16_t *>(tile + lane * TP);
+      uint16_t *row = reinterpret_cast<uint16_t *>(tbase + lane * TP);
       int y0 = 0, y2 = 0;
       if (ds > 0) y0 = row[ds - 1];
       if (ds < D - 1) y2 = row[ds + 1];
@@ -352,35 +512,26 @@ __global__ void __launch_bounds__(128) aggr_kernel(const AggrArgs a) {
     __syncwarp();
   };
 
-  int slot = 0;
-  uint32_t parity = 0;
-  for (int ci = 0; ci < nchunks; ++ci) {
-    mbar_wait(bar0 + 8 * slot, parity);
-    if (ci + NCH - 1 < nchunks) issue(ci + NCH - 1); // refills the slot consumed one chunk ago
-    const int s0 = ci * K;
-    const int kc = min(K, steps - s0);
-    const unsigned char *pc = ring + slot * K * PIECE + loff;
-    if (kc == K) {
-      if (hrev) {
-        pc += (K - 1) * PIECE;
-#pragma unroll
-        for (int k = 0; k < K; ++k) { step(s0 + k, pc); pc -= PIECE; }
-      } else {
-#pragma unroll
-        for (int k = 0; k < K; ++k) { step(s0 + k, pc); pc += PIECE; }
-      }
+  for (int t = 0; t < ntiles; ++t) {
+    const int ts = t % WTA_TILES;
+    mbar_wait(barFull + 8 * ts, (uint32_t)((t / WTA_TILES) & 1));
+    const int t0 = t * 32;
+    const int cnt = min(32, steps - t0);
+    unsigned char *tbase = tile + ts * 32 * TP;
+    const unsigned char *trow = tbase + loff;
+    if (cnt == 32) {
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) { cstep(trow, k); trow += TP; }
     } else {
-      const int dp = hrev ? -PIECE : PIECE;
-      if (hrev) pc += (kc - 1) * PIECE;
-      for (int k = 0; k < kc; ++k) { step(s0 + k, pc); pc += dp; }
+      for (int k = 0; k < cnt; ++k) { cstep(trow, k); trow += TP; }
     }
-    if (MODE == 2) {
-      const int done = s0 + kc;
-      if ((done & 31) == 0 || done == steps) tile_phase((done - 1) & ~31, done - ((done - 1) & ~31));
+    tile_phase(tbase, t0, cnt);
+    if (lane == 0) {
+      const uint32_t bar = barEmpty + 8 * ts;
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
     }
-    if (++slot == NCH) { slot = 0; parity ^= 1; }
   }
-  if (MODE == 2 && active) {
+  if (active) {
     // pixels whose diagonal leaves the image on the right: x' = cols-1-d, d < D-1
 #pragma unroll
     for (int k = 0; k < DPL; ++k) {
@@ -391,30 +542,42 @@ __global__ void __launch_bounds__(128) aggr_kernel(const AggrArgs a) {
   }
 }
 
-template <int NR, int MODE, bool PARTIAL>
-static cudaError_t launch_one(const AggrArgs &a, int wpb, cudaStream_t st) {
-  constexpr int K0 = NR <= 16 ? (32 / NR < 2 ? 2 : 32 / NR) : 2;
-  constexpr int K = MODE == 1 ? (K0 >= 4 ? K0 / 2 : K0) : K0;
-  constexpr int NCH = MODE == 0 ? 4 : 3;
+template <int NR> struct AggrCfg {
+  static constexpr int K0 = 32 / NR < 2 ? 2 : 32 / NR;
+  template <int MODE> static constexpr int K() { return MODE == 1 ? (K0 >= 4 ? K0 / 2 : K0) : K0; }
+  template <int MODE> static constexpr int NCH() { return MODE == 0 ? 4 : 3; }
+};
+
+template <int NR, int MODE, bool PARTIAL, bool DBG>
+static cudaError_t launch_one(const AggrArgs &a, cudaStream_t st) {
+  constexpr int K = AggrCfg<NR>::template K<MODE>();
+  constexpr int NCH = AggrCfg<NR>::template NCH<MODE>();
+  const size_t smem = (size_t)aggr_smem<MODE, K, NCH>(a.D).total; // one path per block
   const long npaths = (long)a.N * (a.vertical ? a.cols : a.rows);
-  const unsigned blocks = (unsigned)((npaths + wpb - 1) / wpb);
-  const size_t smem = (size_t)wpb * aggr_smem<MODE, K, NCH>(a.D).total;
-  auto k = aggr_kernel<NR, MODE, PARTIAL, K, NCH>;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+  cudaError_t e;
+  if constexpr (MODE == 2) {
+    auto k = aggr_wta_kernel<NR, PARTIAL, DBG, K, NCH>;
+    if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    k<<<(unsigned)npaths, 64, smem, st>>>(a);
+  } else {
+    auto k = aggr_kernel<NR, MODE, PARTIAL, DBG, K, NCH>;
+    if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    k<<<(unsigned)npaths, 32, smem, st>>>(a);
   }
-  k<<<blocks, wpb * 32, smem, st>>>(a);
   return cudaGetLastError();
 }
 
 static int nr_for(int D) { return D <= 64 ? 1 : D <= 128 ? 2 : D <= 256 ? 4 : D <= 512 ? 8 : 16; }
 
-template <int MODE> static cudaError_t dispatch(const AggrArgs &a, int wpb, cudaStream_t st) {
+template <int MODE> static cudaError_t dispatch(const AggrArgs &a, cudaStream_t st) {
   const int nr = nr_for(a.D);
   const bool partial = a.D != 64 * nr;
+  const bool dbg = MODE != 0 && a.dbg0 != nullptr;
 #define SSB_CASE(NRV)                                                                             \
-  case NRV: return partial ? launch_one<NRV, MODE, true>(a, wpb, st) : launch_one<NRV, MODE, false>(a, wpb, st);
+  case NRV:                                                                                       \
+    if (MODE == 0) return partial ? launch_one<NRV, MODE, true, false>(a, st) : launch_one<NRV, MODE, false, false>(a, st); \
+    if (dbg) return partial ? launch_one<NRV, MODE, true, true>(a, st) : launch_one<NRV, MODE, false, true>(a, st);  \
+    return partial ? launch_one<NRV, MODE, true, false>(a, st) : launch_one<NRV, MODE, false, false>(a, st);
   switch (nr) {
     SSB_CASE(1) SSB_CASE(2) SSB_CASE(4) SSB_CASE(8) SSB_CASE(16)
   }
@@ -434,6 +597,7 @@ cudaError_t launch_aggr_wta(const AggrBuffers &b, int N, int rows, int cols, int
                             int uniq, cudaStream_t stream, cudaStream_t s_aux, cudaEvent_t *ev,
                             const AggrMarks *marks) {
   auto mark = [&](const char *name) { if (marks) marks->mark(marks->ctx, name); };
+  if ((long)N * (rows > cols ? rows : cols) > 0x7fffffffL) return cudaErrorInvalidValue;
   AggrArgs a{};
   a.C = b.C;
   a.N = N; a.rows = rows; a.cols = cols; a.D = D;
@@ -446,24 +610,24 @@ cudaError_t launch_aggr_wta(const AggrBuffers &b, int N, int rows, int cols, int
   if ((err = cudaStreamWaitEvent(s_aux, ev[0], 0)) != cudaSuccess) return err;
   AggrArgs h = a;
   h.vertical = 0; h.reverse = 1; h.out = b.L1;
-  if ((err = dispatch<0>(h, 1, s_aux)) != cudaSuccess) return err;
+  if ((err = dispatch<0>(h, s_aux)) != cudaSuccess) return err;
   if ((err = cudaEventRecord(ev[1], s_aux)) != cudaSuccess) return err;
   AggrArgs v = a;
   v.vertical = 1; v.reverse = 0; v.out = b.L2;
-  if ((err = dispatch<0>(v, 1, stream)) != cudaSuccess) return err;
+  if ((err = dispatch<0>(v, stream)) != cudaSuccess) return err;
   mark("aggr_down");
   if ((err = cudaStreamWaitEvent(stream, ev[1], 0)) != cudaSuccess) return err;
   mark("aggr_left_tail"); // time the right->left pass (aux stream) outlives the top->bottom one
   // bottom->top, accumulating L1+L2+L3
   AggrArgs u = a;
   u.vertical = 1; u.reverse = 1; u.aux0 = b.L1; u.aux1 = b.L2; u.out = b.S3; u.dbg0 = b.dbgL3;
-  if ((err = dispatch<1>(u, 1, stream)) != cudaSuccess) return err;
+  if ((err = dispatch<1>(u, stream)) != cudaSuccess) return err;
   mark("aggr_up");
   // left->right + blend + winner-takes-all
   AggrArgs w = a;
   w.vertical = 0; w.reverse = 0; w.aux0 = b.S3; w.dbg0 = b.dbgL0; w.dbg1 = b.dbgLAll;
   w.dispL = b.dispL; w.dispR = b.dispR;
-  err = dispatch<2>(w, 1, stream);
+  err = dispatch<2>(w, stream);
   mark("aggr_right_wta");
   return err;
 }
