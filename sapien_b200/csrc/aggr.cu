@@ -45,6 +45,7 @@ struct AggrArgs {
   int vertical, reverse;
   uint32_t P1P1, P2P2;
   int uniq;
+  int nsm; // SM count: blocks b and b + nsm land on the same SM in the first wave
 };
 
 // ---- mbarrier + bulk-copy (TMA 1-D) primitives -------------------------------------------------
@@ -139,7 +140,7 @@ template <int MODE, int K, int NCH> __host__ __device__ inline AggrSmem aggr_sme
   const int piece = D * 2;
   s.ring = 64; // mbarriers first: NCH bulk-copy barriers, then (MODE 2) WTA_TILES full + WTA_TILES empty
   s.tile = s.ring + nstream<MODE>() * NCH * K * piece;
-  s.gk = s.tile + (MODE == 2 ? WTA_TILES * 32 * (piece + 16) : 0);
+  s.gk = s.tile + (MODE == 2 ? (WTA_TILES * 32 + 1) * (piece + 16) : 0); // +1 row: the consumer prefetches one row ahead
   s.rb = s.gk + (MODE == 2 ? 32 * 4 : 0);
   s.total = s.rb + (MODE == 2 ? 32 * 2 : 0);
   s.total = (s.total + 127) & ~127;
@@ -321,7 +322,10 @@ __global__ void __launch_bounds__(128) aggr_wta_kernel(const AggrArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int role = warp & 1;
+  // Warp slots map to the 4 schedulers of an SM by slot % 4 and a 2-warp block takes two adjacent
+  // slots, so a fixed role order would put every producer of an SM on the same two schedulers.
+  // Blocks b, b+nsm, b+2*nsm share an SM (round-robin first wave): alternate the order with b / nsm.
+  const int role = (warp ^ (blockIdx.x / a.nsm)) & 1;
   const int ppb = blockDim.x >> 6; // paths (rows) per block
   const long path = (long)blockIdx.x * ppb + (warp >> 1);
   const bool valid = path < (long)a.N * a.rows;
@@ -439,11 +443,7 @@ __global__ void __launch_bounds__(128) aggr_wta_kernel(const AggrArgs a) {
   const uint32_t firstmask = lane == 0 ? 0xffffffffu : 0u;
   const bool last_lane = lane == nact - 1;
 
-  auto cstep = [&](const unsigned char *trow, int k) {
-    uint32_t la[NR];
-#pragma unroll
-    for (int r = 0; r < NR; ++r) la[r] = 0;
-    if (active) lds_vec<NR>(trow, la);
+  auto cstep = [&](const uint32_t (&la)[NR], int k) {
     // keys (value << 16 | d): u32 min == lowest value, then lowest d (wta.cu:30-65)
     uint32_t key[DPL];
 #pragma unroll
@@ -463,6 +463,11 @@ __global__ void __launch_bounds__(128) aggr_wta_kernel(const AggrArgs a) {
     T[0] = min(upT, key[0]);
     if (last_lane) rbuf[k] = (uint16_t)T[DPL - 1]; // pixel s-(D-1), stored by the tile phase
   };
+  auto load_row = [&](const unsigned char *trow, uint32_t (&la)[NR]) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) la[r] = 0;
+    if (active) lds_vec<NR>(trow, la);
+  };
 
   // one lane per pixel: uniqueness + sub-pixel for the (up to 32) pixels of the finished tile
   auto tile_phase = [&](unsigned char *tbase, int t0, int cnt) {
@@ -480,13 +485,22 @@ __global__ void __launch_bounds__(128) aggr_wta_kernel(const AggrArgs a) {
         if (ds > 0) row[ds - 1] = 0xffffu;
         row[ds] = 0xffffu;
         if (ds < D - 1) row[ds + 1] = 0xffffu;
-        uint32_t mn = 0xffffffffu;
+        uint32_t mn0 = 0xffffffffu, mn1 = 0xffffffffu, mn2 = 0xffffffffu, mn3 = 0xffffffffu;
         const uint4 *r4 = reinterpret_cast<const uint4 *>(row);
-        for (int i = 0; i < D / 8; ++i) {
-          const uint4 v = r4[i];
-          mn = __vimin3_u16x2(mn, v.x, v.y);
-          mn = __vimin3_u16x2(mn, v.z, v.w);
+        int i = 0;
+        for (; i + 4 <= D / 8; i += 4) { // 4 independent chains: the loads of one round overlap
+          const uint4 v0 = r4[i], v1 = r4[i + 1], v2 = r4[i + 2], v3 = r4[i + 3];
+          mn0 = __vimin3_u16x2(mn0, v0.x, v0.y); mn1 = __vimin3_u16x2(mn1, v1.x, v1.y);
+          mn2 = __vimin3_u16x2(mn2, v2.x, v2.y); mn3 = __vimin3_u16x2(mn3, v3.x, v3.y);
+          mn0 = __vimin3_u16x2(mn0, v0.z, v0.w); mn1 = __vimin3_u16x2(mn1, v1.z, v1.w);
+          mn2 = __vimin3_u16x2(mn2, v2.z, v2.w); mn3 = __vimin3_u16x2(mn3, v3.z, v3.w);
         }
+        for (; i < D / 8; ++i) {
+          const uint4 v = r4[i];
+          mn0 = __vimin3_u16x2(mn0, v.x, v.y);
+          mn1 = __vimin3_u16x2(mn1, v.z, v.w);
+        }
+        const uint32_t mn = __vimin3_u16x2(mn0, mn1, __vminu2(mn2, mn3));
         const int m2 = (int)min(mn & 0xffffu, mn >> 16);
         ok = m2 * k100u >= m * 100;
       } else { // uniqueness_ratio >= 100: the product test is not monotone; evaluate it literally
@@ -519,11 +533,23 @@ __global__ void __launch_bounds__(128) aggr_wta_kernel(const AggrArgs a) {
     const int cnt = min(32, steps - t0);
     unsigned char *tbase = tile + ts * 32 * TP;
     const unsigned char *trow = tbase + loff;
+    uint32_t cur[NR], nxt[NR];
+    load_row(trow, cur);
     if (cnt == 32) {
 #pragma unroll 8
-      for (int k = 0; k < 32; ++k) { cstep(trow, k); trow += TP; }
+      for (int k = 0; k < 32; ++k) { // the next row's load is in flight while this one is processed
+        trow += TP;
+        load_row(trow, nxt); // k == 31 reads the row after the tile: inside the tile ring or gk/rb area
+        cstep(cur, k);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) cur[r] = nxt[r];
+      }
     } else {
-      for (int k = 0; k < cnt; ++k) { cstep(trow, k); trow += TP; }
+      for (int k = 0; k < cnt; ++k) {
+        cstep(cur, k);
+        trow += TP;
+        load_row(trow, cur);
+      }
     }
     tile_phase(tbase, t0, cnt);
     if (lane == 0) {
@@ -604,6 +630,15 @@ cudaError_t launch_aggr_wta(const AggrBuffers &b, int N, int rows, int cols, int
   a.P1P1 = (uint32_t)P1 * 0x10001u;
   a.P2P2 = (uint32_t)P2 * 0x10001u;
   a.uniq = uniq;
+  {
+    static int nsm = 0;
+    if (nsm == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) nsm = 148;
+    }
+    a.nsm = nsm;
+  }
   cudaError_t err;
   // fork: right->left on the aux stream, top->bottom on the main stream
   if ((err = cudaEventRecord(ev[0], stream)) != cudaSuccess) return err;

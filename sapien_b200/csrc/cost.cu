@@ -223,13 +223,14 @@ static cudaError_t launch_cfg(const uint32_t *cL, const uint32_t *cR, uint16_t *
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, TD * NS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   const int nchunks = (D + 2 * TD - 1) / (2 * TD);
   const long xb = (long)((cols + NS * TX - 1) / (NS * TX)) * nchunks;
-  // Row bands: as many as fit in ONE resident wave (no tail), at least 24 rows each so that the
-  // BH-1 warm-up rows stay a small overhead; big batches simply use 64-row bands.
+  // Row bands: as many as fit in ONE resident wave (a second, partial wave would double the
+  // kernel time), at least 24 rows each so that the BH-1 warm-up rows stay a small overhead.
+  // Batches that exceed one wave anyway use ~64-row bands.
   const long capacity = (long)g_sm_count * per_sm;
   long bands = capacity / (xb * N);
-  const long max_bands = (rows + 23) / 24, min_bands = (rows + 63) / 64;
+  const long max_bands = (rows + 23) / 24;
   if (bands > max_bands) bands = max_bands;
-  if (bands < min_bands) bands = min_bands;
+  if (bands < 1) bands = (rows + 63) / 64;
   const int ry = (int)((rows + bands - 1) / bands);
   dim3 grid((unsigned)xb, (unsigned)((rows + ry - 1) / ry), (unsigned)N);
   k<<<grid, dim3(TD, NS), smem, st>>>(cL, cR, C, rows, cols, D, nchunks, ry);
