@@ -22,7 +22,7 @@
 
 namespace ssb {
 
-template <int BW, int BH, int TX, int NS, int TD, bool EDGE>
+template <int BW, int BH, int TX, int NS, int TD, bool EDGE, bool PACK8>
 __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, const uint32_t *__restrict__ imR,
                                           uint16_t *__restrict__ outC, int rows, int cols, int D, int dbase,
                                           int xblk, int y_begin, int y_end, uint32_t *ring,
@@ -32,7 +32,8 @@ __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, cons
   constexpr int NXW = NS * TX + BW - 1; // left census codes staged per block
   constexpr int DC = 2 * TD;            // disparities per chunk
   constexpr int NRC = NXW + DC + 1;     // right census codes staged per block
-  constexpr int SLOT = NS * TX * TD;    // ring words per input row
+  constexpr int SLOT = NS * TX * TD / (PACK8 ? 2 : 1); // ring words per input row
+  constexpr int XW = PACK8 ? TX / 2 : TX;              // ring words per thread and row
   constexpr int nthreads = TD * NS;
   constexpr int NLD = (NRC + nthreads - 1) / nthreads;
   constexpr int SLS = (NXW + 3) & ~3, SRS = (NRC + 3) & ~3; // row strides keep vector loads aligned
@@ -72,7 +73,7 @@ __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, cons
   uint32_t vacc[TX];
 #pragma unroll
   for (int x = 0; x < TX; ++x) vacc[x] = 0;
-  uint32_t *myring = ring + (size_t)strip * TX * TD + td;
+  uint32_t *myring = ring + (size_t)strip * XW * TD + td;
   const int ib = strip * TX; // staged index of my first hamming column
   // output cursor: element (y, xs+HW+ib, d_lo) of the first emitted row
   const int xo0 = xs + HW + ib;
@@ -118,12 +119,26 @@ __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, cons
       uint32_t hs = 0;
 #pragma unroll
       for (int i = 0; i < BW - 1; ++i) hs += h[i];
+      // ring entry: the horizontal sum of this input row.  PACK8: both halves of hs are < 256
+      // (BW * census bits <= 255), so two columns share one word (bytes A.lo, A.hi, B.lo, B.hi).
+      uint32_t hprev = 0;
+      auto ring_put = [&](int x, uint32_t v) {
+        if (!PACK8) rs_w[x * TD] = v;
+        else if (x & 1) rs_w[(x >> 1) * TD] = __byte_perm(hprev, v, 0x6420);
+        else hprev = v;
+      };
+      uint32_t wold = 0;
+      auto ring_get = [&](int x) -> uint32_t {
+        if (!PACK8) return rs_r[x * TD];
+        if (!(x & 1)) { wold = rs_r[(x >> 1) * TD]; return __byte_perm(wold, 0u, 0x4140); }
+        return __byte_perm(wold, 0u, 0x4342);
+      };
       if (it < BH - 1) {
 #pragma unroll
         for (int x = 0; x < TX; ++x) {
           hs += h[x + BW - 1];
           vacc[x] += hs;
-          rs_w[x * TD] = hs;
+          ring_put(x, hs);
           hs -= h[x];
         }
       } else {
@@ -132,7 +147,7 @@ __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, cons
         for (int x = 0; x < TX; ++x) {
           hs += h[x + BW - 1];
           vacc[x] += hs;
-          rs_w[x * TD] = hs;
+          ring_put(x, hs);
           hs -= h[x];
           if (!EDGE || xo0 + x < cols) {
             if (even_d) {
@@ -143,7 +158,7 @@ __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, cons
             }
           }
           dst += D;
-          vacc[x] -= rs_r[x * TD]; // the row that leaves the window before the next input
+          vacc[x] -= ring_get(x); // the row that leaves the window before the next input
         }
         prow += rowpitch;
       }
@@ -154,7 +169,7 @@ __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, cons
   }
 }
 
-template <int BW, int BH, int TX, int NS, int TD>
+template <int BW, int BH, int TX, int NS, int TD, bool PACK8>
 __global__ void __launch_bounds__(TD *NS)
 cost_kernel(const uint32_t *__restrict__ cL, const uint32_t *__restrict__ cR,
             uint16_t *__restrict__ C, int rows, int cols, int D, int nchunks, int ry) {
@@ -172,9 +187,9 @@ cost_kernel(const uint32_t *__restrict__ cL, const uint32_t *__restrict__ cR,
   uint16_t *outC = C + (size_t)n * rows * cols * D;
   const bool edge = (xblk + 1) * (NS * TX) + BW / 2 > cols; // needs the replicate-border hold / x bound
   if (edge)
-    cost_band<BW, BH, TX, NS, TD, true>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR);
+    cost_band<BW, BH, TX, NS, TD, true, PACK8>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR);
   else
-    cost_band<BW, BH, TX, NS, TD, false>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR);
+    cost_band<BW, BH, TX, NS, TD, false, PACK8>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR);
 }
 
 // Any block size: direct evaluation (bw*bh POPC per output).  Only used for block sizes that have
@@ -206,11 +221,11 @@ __global__ void cost_generic_kernel(const uint32_t *__restrict__ cL, const uint3
 
 static int g_sm_count = 0;
 
-template <int BW, int BH, int TX, int NS, int TD>
+template <int BW, int BH, int TX, int NS, int TD, bool PACK8>
 static cudaError_t launch_cfg(const uint32_t *cL, const uint32_t *cR, uint16_t *C, int N, int rows,
                               int cols, int D, cudaStream_t st) {
-  auto k = cost_kernel<BW, BH, TX, NS, TD>;
-  const size_t smem = (size_t)BH * NS * TX * TD * sizeof(uint32_t);
+  auto k = cost_kernel<BW, BH, TX, NS, TD, PACK8>;
+  const size_t smem = (size_t)BH * NS * TX * TD * sizeof(uint32_t) / (PACK8 ? 2 : 1);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (g_sm_count == 0) {
@@ -239,20 +254,25 @@ static cudaError_t launch_cfg(const uint32_t *cL, const uint32_t *cR, uint16_t *
 
 template <int BW, int BH>
 static cudaError_t launch_fast(const uint32_t *cL, const uint32_t *cR, uint16_t *C, int N, int rows,
-                               int cols, int D, cudaStream_t st) {
+                               int cols, int D, int bits, cudaStream_t st) {
   constexpr int TX = 16;
-  if (D <= 64) return launch_cfg<BW, BH, TX, 4, 32>(cL, cR, C, N, rows, cols, D, st);
-  return launch_cfg<BW, BH, TX, 2, 64>(cL, cR, C, N, rows, cols, D, st);
+  // a BW-wide Hamming sum fits one byte: half-size ring (BH == 1 reads back the word it is writing)
+  const bool pack8 = BH > 1 && BW * bits <= 255;
+  if (D <= 64)
+    return pack8 ? launch_cfg<BW, BH, TX, 4, 32, true>(cL, cR, C, N, rows, cols, D, st)
+                 : launch_cfg<BW, BH, TX, 4, 32, false>(cL, cR, C, N, rows, cols, D, st);
+  return pack8 ? launch_cfg<BW, BH, TX, 2, 64, true>(cL, cR, C, N, rows, cols, D, st)
+               : launch_cfg<BW, BH, TX, 2, 64, false>(cL, cR, C, N, rows, cols, D, st);
 }
 
 cudaError_t launch_cost(const uint32_t *cL, const uint32_t *cR, uint16_t *C, int N, int rows,
-                        int cols, int D, int bw, int bh, cudaStream_t st) {
+                        int cols, int D, int bw, int bh, int bits, cudaStream_t st) {
   if (N > 65535) return cudaErrorInvalidValue;
-  if (bw == 7 && bh == 7) return launch_fast<7, 7>(cL, cR, C, N, rows, cols, D, st);
-  if (bw == 1 && bh == 1) return launch_fast<1, 1>(cL, cR, C, N, rows, cols, D, st);
-  if (bw == 3 && bh == 3) return launch_fast<3, 3>(cL, cR, C, N, rows, cols, D, st);
-  if (bw == 5 && bh == 5) return launch_fast<5, 5>(cL, cR, C, N, rows, cols, D, st);
-  if (bw == 9 && bh == 9) return launch_fast<9, 9>(cL, cR, C, N, rows, cols, D, st);
+  if (bw == 7 && bh == 7) return launch_fast<7, 7>(cL, cR, C, N, rows, cols, D, bits, st);
+  if (bw == 1 && bh == 1) return launch_fast<1, 1>(cL, cR, C, N, rows, cols, D, bits, st);
+  if (bw == 3 && bh == 3) return launch_fast<3, 3>(cL, cR, C, N, rows, cols, D, bits, st);
+  if (bw == 5 && bh == 5) return launch_fast<5, 5>(cL, cR, C, N, rows, cols, D, bits, st);
+  if (bw == 9 && bh == 9) return launch_fast<9, 9>(cL, cR, C, N, rows, cols, D, bits, st);
   const size_t total = (size_t)N * rows * cols * D;
   const unsigned blocks = (unsigned)((total + 255) / 256);
   cost_generic_kernel<<<blocks, 256, 0, st>>>(cL, cR, C, rows, cols, D, bw, bh, total);

@@ -248,7 +248,8 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
     fp.seed = c.ir_noise_seed; fp.frame = e->frame;
     CK(launch_front(fp, st));
     e->mark("front");
-    CK(launch_cost(fp.census0, fp.census1, e->C, wn, rows, cols, D, c.bf_width, c.bf_height, st));
+    CK(launch_cost(fp.census0, fp.census1, e->C, wn, rows, cols, D, c.bf_width, c.bf_height,
+                   census_bits(c.census_width, c.census_height), st));
     e->mark("cost");
     AggrBuffers ab{};
     ab.C = e->C; ab.L1 = e->L1; ab.L2 = e->L2; ab.S3 = e->S3;

@@ -28,9 +28,10 @@ struct FrontParams {
 cudaError_t launch_front(const FrontParams &p, cudaStream_t stream);
 
 // ----------------------------------------------------------------------------- cost.cu
-// C[n][y][x][d] = sum over the bw x bh replicate-border block of popc(cL(y,x) ^ cR(y,max(x-d,0)))
+// C[n][y][x][d] = sum over the bw x bh replicate-border block of popc(cL(y,x) ^ cR(y,max(x-d,0)));
+// bits = number of significant census bits (upper bound of one Hamming distance)
 cudaError_t launch_cost(const uint32_t *cL, const uint32_t *cR, uint16_t *C, int N, int rows,
-                        int cols, int D, int bw, int bh, cudaStream_t stream);
+                        int cols, int D, int bw, int bh, int bits, cudaStream_t stream);
 
 // ----------------------------------------------------------------------------- aggr.cu
 // true when the packed-u16 DPX path is valid for this configuration
