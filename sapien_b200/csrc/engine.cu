@@ -246,6 +246,9 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
     fp.speckle_shape = c.speckle_shape; fp.speckle_scale = c.speckle_scale;
     fp.gaussian_mu = c.gaussian_mu; fp.gaussian_sigma = c.gaussian_sigma;
     fp.seed = c.ir_noise_seed; fp.frame = e->frame;
+    if (c.registration && w0 == 0) { // the canvas of the whole batch is filled by the first wave's front-end
+      fp.canvas = e->canvas; fp.canvas_n = (size_t)c.batch * e->rsz(); fp.canvas_fill = c.max_depth;
+    }
     CK(launch_front(fp, st));
     e->mark("front");
     CK(launch_cost(fp.census0, fp.census1, e->C, wn, rows, cols, D, c.bf_width, c.bf_height,
@@ -279,6 +282,7 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
   pp.a1 = e->a1; pp.a2 = e->a2; pp.a3 = e->a3; pp.b1 = c.b1; pp.b2 = c.b2; pp.b3 = c.b3;
   pp.rgb_rows = (int)c.rgb_rows; pp.rgb_cols = (int)c.rgb_cols;
   pp.canvas = e->canvas; pp.out = e->out;
+  pp.canvas_prefilled = 1;
   int pl = 0;
   CK(launch_post(pp, st, &pl));
   launches += pl;

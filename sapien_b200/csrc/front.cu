@@ -113,6 +113,14 @@ __global__ void __launch_bounds__(FT *FTY) front_kernel(const FrontParams p) {
   const int n = blockIdx.z;
   const int x0 = blockIdx.x * FT, y0 = blockIdx.y * FT;
   const int tid = threadIdx.y * FT + threadIdx.x;
+  if (p.canvas) { // grid-stride fill of the registration canvas (float4 stores; tail by scalars)
+    const size_t nthr = (size_t)gridDim.x * gridDim.y * gridDim.z * (FT * FTY);
+    const size_t gtid = (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (FT * FTY) + tid;
+    const size_t n4 = p.canvas_n / 4;
+    const float4 f4 = make_float4(p.canvas_fill, p.canvas_fill, p.canvas_fill, p.canvas_fill);
+    for (size_t i = gtid; i < n4; i += nthr) reinterpret_cast<float4 *>(p.canvas)[i] = f4;
+    for (size_t i = n4 * 4 + gtid; i < p.canvas_n; i += nthr) p.canvas[i] = p.canvas_fill;
+  }
   const Src sl{p.left_u8, p.left_rgba, p.mapLx, p.mapLy};
   const Src sr{p.right_u8, p.right_rgba, p.mapRx, p.mapRy};
   for (int i = tid; i < wc * wr; i += FT * FTY) {

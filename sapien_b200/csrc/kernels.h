@@ -24,6 +24,11 @@ struct FrontParams {
   float speckle_shape, speckle_scale, gaussian_mu, gaussian_sigma;
   uint64_t seed;
   uint64_t frame; // frame counter (decorrelates successive frames)
+  // optional: fill the registration canvas [canvas_n floats] with canvas_fill (initRgbDepth,
+  // camera.cu:170-177) while the front-end runs, instead of a launch of its own
+  float *canvas;
+  size_t canvas_n;
+  float canvas_fill;
 };
 cudaError_t launch_front(const FrontParams &p, cudaStream_t stream);
 
@@ -80,6 +85,7 @@ struct PostParams {
   float b1, b2, b3;
   int rgb_rows, rgb_cols;
   float *canvas;   // [N][rgb_rows][rgb_cols] splat target
+  int canvas_prefilled; // 1: the front-end kernel already filled the canvas with max_depth
   float *out;      // final depth: [N][rgb_rows][rgb_cols] or [N][frows][fcols]
 };
 cudaError_t launch_post(const PostParams &p, cudaStream_t stream, int *launches);

@@ -33,7 +33,30 @@ template <int N> __device__ __forceinline__ void bitonic_sort(float (&a)[N]) {
 
 constexpr int PT_X = 32, PT_Y = 8;
 
-template <int K>
+__device__ __forceinline__ float atomic_min_float(float *addr, float value) { // camera.cu:42-47
+  return (value >= 0) ? __int_as_float(atomicMin((int *)addr, __float_as_int(value)))
+                      : __uint_as_float(atomicMax((unsigned int *)addr, __float_as_uint(value)));
+}
+
+// disparity -> depth (camera.cu:160-168) and, with registration, the forward splat into the RGB
+// frame (camera.cu:179-196); same expression shapes as the reference so nvcc contracts identically.
+__device__ __forceinline__ void depth_and_splat(const PostParams &p, size_t n, size_t pos, float d) {
+  const size_t idx = n * (size_t)p.frows * p.fcols + pos;
+  const float z = (d <= 0) ? 0 : p.focal * p.baseline / d;
+  p.depth[idx] = z;
+  if (p.registration) {
+    const float zRgb = p.a3[pos] * z + p.b3;
+    const int x = (int)roundf((p.a1[pos] * z + p.b1) / zRgb);
+    const int y = (int)roundf((p.a2[pos] * z + p.b2) / zRgb);
+    if (zRgb > 0 && x >= 0 && x < p.rgb_cols && y >= 0 && y < p.rgb_rows)
+      atomic_min_float(p.canvas + (n * p.rgb_rows + y) * p.rgb_cols + x, zRgb);
+  } else {
+    p.out[idx] = (z < p.min_depth || z >= p.max_depth) ? 0.0f : z; // camera.cu:237-239
+  }
+}
+
+// FUSE: no ROI -> the matched image is the full image, so depth + splat run in the same thread.
+template <int K, bool FUSE>
 __global__ void __launch_bounds__(PT_X *PT_Y) lr_median_kernel(const PostParams p) {
   constexpr int H = K / 2;
   constexpr int WC = PT_X + 2 * H, WR = PT_Y + 2 * H;
@@ -75,40 +98,23 @@ __global__ void __launch_bounds__(PT_X *PT_Y) lr_median_kernel(const PostParams 
     out = a[NN / 2];
   }
   p.disp_med[img + (size_t)y * p.cols + x] = out;
-  if (p.bbox)
-    p.disp_full[((size_t)n * p.frows + (y + p.by)) * p.fcols + x + p.bx] = out;
+  if (FUSE) depth_and_splat(p, (size_t)n, (size_t)y * p.cols + x, out);
+  else if (p.bbox) p.disp_full[((size_t)n * p.frows + (y + p.by)) * p.fcols + x + p.bx] = out;
 }
 
 // ------------------------------------------------------------------ depth + registration splat
-__device__ __forceinline__ float atomic_min_float(float *addr, float value) { // camera.cu:42-47
-  return (value >= 0) ? __int_as_float(atomicMin((int *)addr, __float_as_int(value)))
-                      : __uint_as_float(atomicMax((unsigned int *)addr, __float_as_uint(value)));
-}
-
 __global__ void fill_kernel(float *dst, size_t n, float v) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) dst[i] = v;
 }
 
-__global__ void __launch_bounds__(256) depth_splat_kernel(const PostParams p) {
+__global__ void __launch_bounds__(256) depth_splat_kernel(const PostParams p) { // ROI mode only
   const size_t fsz = (size_t)p.frows * p.fcols;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= fsz * p.N) return;
   const size_t n = idx / fsz;
-  const size_t pos = idx - n * fsz;
-  const float d = p.disp_full[idx];
-  const float z = (d <= 0) ? 0 : p.focal * p.baseline / d; // camera.cu:167
-  p.depth[idx] = z;
-  if (p.registration) { // camera.cu:187-195, same expression shapes so nvcc contracts identically
-    const float zRgb = p.a3[pos] * z + p.b3;
-    const int x = (int)roundf((p.a1[pos] * z + p.b1) / zRgb);
-    const int y = (int)roundf((p.a2[pos] * z + p.b2) / zRgb);
-    if (zRgb > 0 && x >= 0 && x < p.rgb_cols && y >= 0 && y < p.rgb_rows)
-      atomic_min_float(p.canvas + (n * p.rgb_rows + y) * p.rgb_cols + x, zRgb);
-  } else {
-    p.out[idx] = (z < p.min_depth || z >= p.max_depth) ? 0.0f : z; // camera.cu:237-239
-  }
+  depth_and_splat(p, n, idx - n * fsz, p.disp_full[idx]);
 }
 
 // Dilation with snapshot semantics + range clamp, canvas -> out.
@@ -138,22 +144,27 @@ cudaError_t launch_post(const PostParams &p, cudaStream_t st, int *launches) {
   if (p.bbox) { // outside-ROI disparity is defined as 0 (reference leaves it uninitialised)
     if ((err = cudaMemsetAsync(p.disp_full, 0, fsz * sizeof(float), st)) != cudaSuccess) return err;
   }
-  if (p.registration) {
+  if (p.registration && !p.canvas_prefilled) {
     fill_kernel<<<(unsigned)min((rsz + 255) / 256, (size_t)148 * 16), 256, 0, st>>>(p.canvas, rsz, p.max_depth);
     ++nl;
   }
   const dim3 grid((p.cols + PT_X - 1) / PT_X, (p.rows + PT_Y - 1) / PT_Y, p.N);
   const dim3 block(PT_X, PT_Y);
+#define SSB_MED(KK)                                                                               \
+  case KK:                                                                                        \
+    if (p.bbox) lr_median_kernel<KK, false><<<grid, block, 0, st>>>(p);                           \
+    else lr_median_kernel<KK, true><<<grid, block, 0, st>>>(p);                                   \
+    break;
   switch (p.mf_size) {
-  case 1: lr_median_kernel<1><<<grid, block, 0, st>>>(p); break;
-  case 3: lr_median_kernel<3><<<grid, block, 0, st>>>(p); break;
-  case 5: lr_median_kernel<5><<<grid, block, 0, st>>>(p); break;
-  case 7: lr_median_kernel<7><<<grid, block, 0, st>>>(p); break;
+    SSB_MED(1) SSB_MED(3) SSB_MED(5) SSB_MED(7)
   default: return cudaErrorInvalidValue;
   }
+#undef SSB_MED
   ++nl;
-  depth_splat_kernel<<<(unsigned)((fsz + 255) / 256), 256, 0, st>>>(p);
-  ++nl;
+  if (p.bbox) {
+    depth_splat_kernel<<<(unsigned)((fsz + 255) / 256), 256, 0, st>>>(p);
+    ++nl;
+  }
   if (p.registration) {
     dilate_range_kernel<<<(unsigned)((rsz + 255) / 256), 256, 0, st>>>(p);
     ++nl;
