@@ -69,6 +69,14 @@ __device__ float gamma_mt(float shape, float scale, Philox &g) {
   return d * scale * boost;
 }
 
+// IR speckle + thermal noise of one source texel (camera.cu:66-74)
+__device__ __noinline__ int ir_noise(const FrontParams &p, int v, size_t sp, int which) {
+  Philox g(p.seed + (uint64_t)which, (uint64_t)sp, p.frame);
+  const float r = roundf((float)v * gamma_mt(p.speckle_shape, p.speckle_scale, g) + p.gaussian_mu +
+                         p.gaussian_sigma * g.normal());
+  return min(max((int)r, 0), 255);
+}
+
 struct Src {
   const uint8_t *u8;
   const float *rgba;
@@ -95,12 +103,7 @@ __device__ __forceinline__ int fetch(const FrontParams &p, const Src &s, int n, 
   } else {
     v = __ldg(s.u8 + sp);
   }
-  if (p.speckle_shape > 0.0f) { // camera.cu:66-74
-    Philox g(p.seed + (uint64_t)which, (uint64_t)sp, p.frame);
-    const float r = roundf((float)v * gamma_mt(p.speckle_shape, p.speckle_scale, g) + p.gaussian_mu +
-                           p.gaussian_sigma * g.normal());
-    v = min(max((int)r, 0), 255);
-  }
+  if (p.speckle_shape > 0.0f) v = ir_noise(p, v, sp, which);
   return v;
 }
 
@@ -159,8 +162,176 @@ __global__ void __launch_bounds__(FT *FTY) front_kernel(const FrontParams p) {
   }
 }
 
+// ---- 7x7 census fast path ------------------------------------------------------------------------
+// Tile of 64 x 32 pixels per 128-thread block; a thread produces the codes of 4 adjacent pixels in 4
+// rows for both images.  The window is staged as BYTES (one fetch through map / ROI / conversion per
+// window texel, fully unrolled so the dependent map -> texel loads of all 22 rounds are in flight
+// together), and the 24 comparisons of csct.cu:61-86 run 4 pixels at a time on packed bytes:
+// ge(a,b) per byte lands in bit 7, and "acc = acc >> 1 | ge & 0x80808080" collects 8 consecutive
+// code bits per byte lane, i.e. one byte of the code of each of the 4 pixels.
+constexpr int F7_TW = 64, F7_TH = 32;
+constexpr int F7_WB = F7_TW + 8; // staged bytes per window row: columns X0-4 .. X0+67
+constexpr int F7_WH = F7_TH + 6; // staged rows: Y0-3 .. Y0+34
+constexpr int F7_NT = 128;
+
+__device__ __forceinline__ uint32_t bytes_ge_bit7(uint32_t a, uint32_t b) {
+  // per byte: bit 7 = (a >= b); other bits unspecified.  (a|H)-(b&~H) cannot borrow across bytes.
+  const uint32_t t = (a | 0x80808080u) - (b & 0x7f7f7f7fu);
+  return (a & ~b) | (~(a ^ b) & t);
+}
+// 4 bytes starting at byte offset o (0..8) of the 12-byte group w0,w1,w2
+template <int O> __device__ __forceinline__ uint32_t bytes_at(uint32_t w0, uint32_t w1, uint32_t w2) {
+  if constexpr (O == 0) return w0;
+  else if constexpr (O == 4) return w1;
+  else if constexpr (O == 8) return w2;
+  else if constexpr (O < 4) return __byte_perm(w0, w1, 0x3210 + 0x1111 * O);
+  else return __byte_perm(w1, w2, 0x3210 + 0x1111 * (O - 4));
+}
+
+template <int I, int J> struct CensusBits {
+  // comparisons (I, J..) of one output row in ascending code-bit order (bit = I*7 + J)
+  static __device__ __forceinline__ void run(const uint32_t (&w)[7][3], uint32_t &acc, uint32_t (&grp)[3]) {
+    constexpr int JMAX = (I == 3) ? 3 : 7;
+    if constexpr (I <= 3 && J < JMAX) {
+      // a = P(y-3+I, x-3+J), b = P(y+3-I, x+3-J); staged column 0 is x0-4, so pixel x0's byte offsets
+      // are 1+J and 7-J
+      const uint32_t a = bytes_at<1 + J>(w[I][0], w[I][1], w[I][2]);
+      const uint32_t b = bytes_at<7 - J>(w[6 - I][0], w[6 - I][1], w[6 - I][2]);
+      acc = ((acc >> 1) & 0x7f7f7f7fu) | (bytes_ge_bit7(a, b) & 0x80808080u); // one SHF + one LOP3
+      constexpr int bit = I * 7 + J;
+      if constexpr ((bit & 7) == 7) grp[bit >> 3] = acc;
+      CensusBits<I, J + 1>::run(w, acc, grp);
+    } else if constexpr (I < 3) {
+      CensusBits<I + 1, 0>::run(w, acc, grp);
+    }
+  }
+};
+
+template <bool RGBA>
+__global__ void __launch_bounds__(F7_NT, 4) front7_kernel(const FrontParams p) {
+  __shared__ __align__(16) uint32_t win[2][F7_WH][F7_WB / 4];
+  const int tid = threadIdx.x;
+  const int n = blockIdx.z;
+  const int X0 = blockIdx.x * F7_TW, Y0 = blockIdx.y * F7_TH;
+  if (p.canvas) { // grid-stride fill of the registration canvas (initRgbDepth, camera.cu:170-177)
+    const size_t nthr = (size_t)gridDim.x * gridDim.y * gridDim.z * F7_NT;
+    const size_t gtid = (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * F7_NT + tid;
+    const size_t n4 = p.canvas_n / 4;
+    const float4 f4 = make_float4(p.canvas_fill, p.canvas_fill, p.canvas_fill, p.canvas_fill);
+    for (size_t i = gtid; i < n4; i += nthr) reinterpret_cast<float4 *>(p.canvas)[i] = f4;
+    for (size_t i = n4 * 4 + gtid; i < p.canvas_n; i += nthr) p.canvas[i] = p.canvas_fill;
+  }
+  const Src sl{p.left_u8, p.left_rgba, p.mapLx, p.mapLy};
+  const Src sr{p.right_u8, p.right_rgba, p.mapRx, p.mapRy};
+  uint8_t *b0 = reinterpret_cast<uint8_t *>(&win[0][0][0]);
+  uint8_t *b1 = reinterpret_cast<uint8_t *>(&win[1][0][0]);
+  constexpr int NEL = F7_WB * F7_WH;
+  constexpr int NRND = (NEL + F7_NT - 1) / F7_NT; // texels per thread and image
+  constexpr int HALF = (NRND + 1) / 2;
+  // Branch-free staging in three straight-line phases (map loads -> texel loads -> convert/store) so
+  // that all loads of a phase are in flight together; out-of-image texels are loaded from a clamped
+  // address and replaced by the zero padding of csct.cu:40-42 afterwards.
+#pragma unroll
+  for (int img = 0; img < 2; ++img) {
+    const Src &s = img ? sr : sl;
+    uint8_t *bdst = img ? b1 : b0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int fx[HALF], fy[HALF];
+      bool inside[HALF];
+      float mx[HALF], my[HALF];
+#pragma unroll
+      for (int k = 0; k < HALF; ++k) {
+        const int e = min((h * HALF + k) * F7_NT + tid, NEL - 1);
+        const int wy = e / F7_WB, wx = e - wy * F7_WB;
+        const int y = Y0 - 3 + wy, x = X0 - 4 + wx;
+        inside[k] = x >= 0 && x < p.cols && y >= 0 && y < p.rows;
+        fx[k] = min(max(x, 0), p.cols - 1) + p.bx;
+        fy[k] = min(max(y, 0), p.rows - 1) + p.by;
+        if (s.mapx) {
+          const size_t mp = (size_t)fy[k] * p.fcols + fx[k];
+          mx[k] = __ldg(s.mapx + mp);
+          my[k] = __ldg(s.mapy + mp);
+        }
+      }
+      float tf[HALF];
+      uint8_t tb[HALF];
+      size_t sp[HALF];
+#pragma unroll
+      for (int k = 0; k < HALF; ++k) {
+        if (s.mapx) { // camera.cu:83-119: always-snapped nearest neighbour
+          const float sx = fminf(fmaxf(roundf(mx[k]), 0.0f), (float)(p.fcols - 1));
+          const float sy = fminf(fmaxf(roundf(my[k]), 0.0f), (float)(p.frows - 1));
+          fx[k] = (int)sx; fy[k] = (int)sy;
+        }
+        sp[k] = ((size_t)n * p.frows + fy[k]) * p.fcols + fx[k];
+        if (RGBA) tf[k] = __ldg(s.rgba + 4 * sp[k]);
+        else tb[k] = __ldg(s.u8 + sp[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < HALF; ++k) {
+        int v;
+        if (RGBA) v = min(max((int)(tf[k] * 255), 0), 255); // truncation, core.cu:51
+        else v = tb[k];
+        if (p.speckle_shape > 0.0f) v = ir_noise(p, v, sp[k], img);
+        const int e = (h * HALF + k) * F7_NT + tid;
+        if (e < NEL) bdst[e] = (uint8_t)(inside[k] ? v : 0);
+      }
+    }
+  }
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4; // 16 x 8 threads, 4 pixels x 4 rows each
+  const int x0 = X0 + 4 * tx;
+  if (x0 >= p.cols) return;
+#pragma unroll
+  for (int img = 0; img < 2; ++img) {
+    uint32_t *census = img ? p.census1 : p.census0;
+    uint8_t *im = img ? p.im1 : p.im0;
+    uint32_t rows_w[10][3]; // window rows 4*ty .. 4*ty+9, words tx, tx+1, tx+2
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) rows_w[r][c] = win[img][4 * ty + r][tx + c];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int y = Y0 + 4 * ty + r;
+      if (y >= p.rows) break;
+      uint32_t w[7][3];
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) w[i][c] = rows_w[r + i][c];
+      }
+      uint32_t acc = 0, grp[3] = {0, 0, 0};
+      CensusBits<0, 0>::run(w, acc, grp);
+      uint32_t code[4];
+      code[0] = (__byte_perm(__byte_perm(grp[0], grp[1], 0x0040), grp[2], 0x0410)) & 0x00ffffffu;
+      code[1] = (__byte_perm(__byte_perm(grp[0], grp[1], 0x0051), grp[2], 0x0510)) & 0x00ffffffu;
+      code[2] = (__byte_perm(__byte_perm(grp[0], grp[1], 0x0062), grp[2], 0x0610)) & 0x00ffffffu;
+      code[3] = (__byte_perm(__byte_perm(grp[0], grp[1], 0x0073), grp[2], 0x0710)) & 0x00ffffffu;
+      const size_t o = ((size_t)n * p.rows + y) * p.cols + x0;
+      const uint32_t centre = w[3][1]; // pixels x0..x0+3 of row y
+      if (x0 + 3 < p.cols && (p.cols & 3) == 0) {
+        *reinterpret_cast<uint4 *>(census + o) = make_uint4(code[0], code[1], code[2], code[3]);
+        *reinterpret_cast<uint32_t *>(im + o) = centre;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (x0 + k < p.cols) { census[o + k] = code[k]; im[o + k] = (uint8_t)(centre >> (8 * k)); }
+      }
+    }
+  }
+}
+
 cudaError_t launch_front(const FrontParams &p, cudaStream_t st) {
   if (p.N > 65535) return cudaErrorInvalidValue;
+  if (p.cw == 7 && p.ch == 7) {
+    const dim3 grid((p.cols + F7_TW - 1) / F7_TW, (p.rows + F7_TH - 1) / F7_TH, p.N);
+    if (p.left_rgba) front7_kernel<true><<<grid, F7_NT, 0, st>>>(p);
+    else front7_kernel<false><<<grid, F7_NT, 0, st>>>(p);
+    return cudaGetLastError();
+  }
   const dim3 grid((p.cols + FT - 1) / FT, (p.rows + FT - 1) / FT, p.N);
   const dim3 block(FT, FTY);
   const size_t smem = 2 * (size_t)(FT + p.cw - 1) * (FT + p.ch - 1);
