@@ -31,6 +31,23 @@ template <int N> __device__ __forceinline__ void bitonic_sort(float (&a)[N]) {
   }
 }
 
+// Median of 9 by the 19-exchange selection network (the result is an order statistic, so any
+// correct network reproduces filter.cu:21-44 bit for bit).
+__device__ __forceinline__ void cswap(float &a, float &b) {
+  const float lo = fminf(a, b), hi = fmaxf(a, b);
+  a = lo; b = hi;
+}
+template <int NP> __device__ __forceinline__ float median9(float (&p)[NP]) {
+  cswap(p[1], p[2]); cswap(p[4], p[5]); cswap(p[7], p[8]);
+  cswap(p[0], p[1]); cswap(p[3], p[4]); cswap(p[6], p[7]);
+  cswap(p[1], p[2]); cswap(p[4], p[5]); cswap(p[7], p[8]);
+  cswap(p[0], p[3]); cswap(p[5], p[8]); cswap(p[4], p[7]);
+  cswap(p[3], p[6]); cswap(p[1], p[4]); cswap(p[2], p[5]);
+  cswap(p[4], p[7]); cswap(p[4], p[2]); cswap(p[6], p[4]);
+  cswap(p[4], p[2]);
+  return p[4];
+}
+
 constexpr int PT_X = 32, PT_Y = 8;
 
 __device__ __forceinline__ float atomic_min_float(float *addr, float value) { // camera.cu:42-47
@@ -65,20 +82,43 @@ __global__ void __launch_bounds__(PT_X *PT_Y) lr_median_kernel(const PostParams 
   const int x0 = blockIdx.x * PT_X, y0 = blockIdx.y * PT_Y;
   const size_t img = (size_t)n * p.rows * p.cols;
   const int tid = threadIdx.y * PT_X + threadIdx.x;
-  for (int i = tid; i < WR * WC; i += PT_X * PT_Y) {
+  // Tile load in straight-line phases (left disparities, then the dependent right-disparity
+  // gathers) so that the loads of all rounds are in flight together.
+  constexpr int NT = PT_X * PT_Y, NEL = WR * WC, NRND = (NEL + NT - 1) / NT;
+  float v[NRND];
+  size_t pos[NRND];
+  int xs[NRND];
+  bool inside[NRND];
+#pragma unroll
+  for (int k = 0; k < NRND; ++k) {
+    const int i = min(k * NT + tid, NEL - 1);
     const int wy = i / WC, wx = i - wy * WC;
     const int y = y0 + wy - H, x = x0 + wx - H;
-    float v = -1.0f;
-    if (x >= 0 && x < p.cols && y >= 0 && y < p.rows) {
-      const size_t pos = img + (size_t)y * p.cols + x;
-      v = p.dispL[pos];
-      if (p.lr_max_diff != 255) { // lrcheck.cu:28-31
-        const int ld = (int)roundf(v);
-        if (ld < 0 || x - ld < 0 || abs(ld - (int)p.dispR[pos - ld]) > p.lr_max_diff) v = -1.0f;
-      }
-      if (p.disp_lr && wy >= H && wy < WR - H && wx >= H && wx < WC - H) p.disp_lr[pos] = v;
+    inside[k] = x >= 0 && x < p.cols && y >= 0 && y < p.rows;
+    xs[k] = min(max(x, 0), p.cols - 1);
+    pos[k] = img + (size_t)min(max(y, 0), p.rows - 1) * p.cols + xs[k];
+    v[k] = p.dispL[pos[k]];
+  }
+  if (p.lr_max_diff != 255) { // lrcheck.cu:28-31
+    int ld[NRND];
+    uint16_t dr[NRND];
+#pragma unroll
+    for (int k = 0; k < NRND; ++k) {
+      ld[k] = (int)roundf(v[k]);
+      dr[k] = p.dispR[pos[k] - min(max(ld[k], 0), xs[k])];
     }
-    tile[wy][wx] = v;
+#pragma unroll
+    for (int k = 0; k < NRND; ++k)
+      if (ld[k] < 0 || xs[k] - ld[k] < 0 || abs(ld[k] - (int)dr[k]) > p.lr_max_diff) v[k] = -1.0f;
+  }
+#pragma unroll
+  for (int k = 0; k < NRND; ++k) {
+    const int i = k * NT + tid;
+    if (i < NEL) {
+      const int wy = i / WC, wx = i - wy * WC;
+      if (p.disp_lr && inside[k] && wy >= H && wy < WR - H && wx >= H && wx < WC - H) p.disp_lr[pos[k]] = v[k];
+      tile[wy][wx] = inside[k] ? v[k] : -1.0f;
+    }
   }
   __syncthreads();
   const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
@@ -92,10 +132,14 @@ __global__ void __launch_bounds__(PT_X *PT_Y) lr_median_kernel(const PostParams 
     for (int j = 0; j < K; ++j)
 #pragma unroll
       for (int i = 0; i < K; ++i) a[j * K + i] = tile[threadIdx.y + j][threadIdx.x + i];
+    if constexpr (K == 3) {
+      out = median9(a);
+    } else {
 #pragma unroll
-    for (int i = NN; i < NP; ++i) a[i] = __int_as_float(0x7f800000);
-    bitonic_sort<NP>(a);
-    out = a[NN / 2];
+      for (int i = NN; i < NP; ++i) a[i] = __int_as_float(0x7f800000);
+      bitonic_sort<NP>(a);
+      out = a[NN / 2];
+    }
   }
   p.disp_med[img + (size_t)y * p.cols + x] = out;
   if (FUSE) depth_and_splat(p, (size_t)n, (size_t)y * p.cols + x, out);
@@ -118,21 +162,53 @@ __global__ void __launch_bounds__(256) depth_splat_kernel(const PostParams p) { 
 }
 
 // Dilation with snapshot semantics + range clamp, canvas -> out.
-__global__ void __launch_bounds__(256) dilate_range_kernel(const PostParams p) {
-  const size_t rsz = (size_t)p.rgb_rows * p.rgb_cols;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rsz * p.N) return;
-  const size_t pos = idx % rsz;
-  const int y = (int)(pos / p.rgb_cols), x = (int)(pos - (size_t)y * p.rgb_cols);
-  float m = p.canvas[idx];
-  if (p.dilation) { // camera.cu:207-227: a pixel < maxDepth lowers its left, top, top-left
-    const bool xr = x + 1 < p.rgb_cols, yb = y + 1 < p.rgb_rows;
-    float t;
-    if (xr && (t = p.canvas[idx + 1]) < p.max_depth) m = fminf(m, t);
-    if (yb && (t = p.canvas[idx + p.rgb_cols]) < p.max_depth) m = fminf(m, t);
-    if (xr && yb && (t = p.canvas[idx + p.rgb_cols + 1]) < p.max_depth) m = fminf(m, t);
+// camera.cu:207-227: a pixel < maxDepth lowers its left, top and top-left neighbours, i.e.
+// out(x,y) = min over the 2x2 block (x..x+1, y..y+1) of the inputs that are < maxDepth.
+// 2-D grid (no index divisions), 4 pixels per thread.
+__global__ void __launch_bounds__(128) dilate_range_kernel(const PostParams p) {
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y;
+  if (x4 >= p.rgb_cols) return;
+  const size_t row = ((size_t)blockIdx.z * p.rgb_rows + y) * p.rgb_cols;
+  const float *r0 = p.canvas + row + x4;
+  const bool yb = y + 1 < p.rgb_rows;
+  const float *r1 = r0 + (yb ? p.rgb_cols : 0);
+  float a[5], b[5];
+  const bool vec = (p.rgb_cols & 3) == 0; // rows are 16-byte aligned and x4+3 < cols
+  if (vec) {
+    const float4 va = *reinterpret_cast<const float4 *>(r0), vb = *reinterpret_cast<const float4 *>(r1);
+    a[0] = va.x; a[1] = va.y; a[2] = va.z; a[3] = va.w;
+    b[0] = vb.x; b[1] = vb.y; b[2] = vb.z; b[3] = vb.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool in = x4 + k < p.rgb_cols;
+      a[k] = in ? r0[k] : p.max_depth;
+      b[k] = in ? r1[k] : p.max_depth;
+    }
   }
-  p.out[idx] = (m < p.min_depth || m >= p.max_depth) ? 0.0f : m;
+  const bool xr = x4 + 4 < p.rgb_cols;
+  a[4] = xr ? r0[4] : p.max_depth;
+  b[4] = xr ? r1[4] : p.max_depth;
+  float o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float m = a[k];
+    if (p.dilation) {
+      if (a[k + 1] < p.max_depth) m = fminf(m, a[k + 1]);
+      if (yb && b[k] < p.max_depth) m = fminf(m, b[k]);
+      if (yb && b[k + 1] < p.max_depth) m = fminf(m, b[k + 1]);
+    }
+    o[k] = (m < p.min_depth || m >= p.max_depth) ? 0.0f : m; // camera.cu:237-239
+  }
+  float *dst = p.out + row + x4;
+  if (vec) {
+    *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (x4 + k < p.rgb_cols) dst[k] = o[k];
+  }
 }
 
 cudaError_t launch_post(const PostParams &p, cudaStream_t st, int *launches) {
@@ -166,7 +242,8 @@ cudaError_t launch_post(const PostParams &p, cudaStream_t st, int *launches) {
     ++nl;
   }
   if (p.registration) {
-    dilate_range_kernel<<<(unsigned)((rsz + 255) / 256), 256, 0, st>>>(p);
+    const dim3 dg((unsigned)((p.rgb_cols + 4 * 128 - 1) / (4 * 128)), (unsigned)p.rgb_rows, (unsigned)p.N);
+    dilate_range_kernel<<<dg, 128, 0, st>>>(p);
     ++nl;
   }
   if (launches) *launches = nl;
