@@ -22,7 +22,7 @@
 
 namespace ssb {
 
-template <int BW, int BH, int TX, int NS, int TD, bool EDGE, bool PACK8>
+template <int BW, int BH, int TX, int NS, int TD, bool EDGE, bool PACK8, bool ODD_D>
 __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, const uint32_t *__restrict__ imR,
                                           uint16_t *__restrict__ outC, int rows, int cols, int D, int dbase,
                                           int xblk, int y_begin, int y_end, uint32_t *ring,
@@ -45,7 +45,6 @@ __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, cons
   const int xs = xblk * (NS * TX) - HW; // image column of staged index 0
   const int imax = cols - 1 - xs;       // staged index of the last image column (replicate border)
   const bool live = d_lo < D;
-  const bool even_d = (D & 1) == 0;
 
   // column indices this thread stages (row-independent).  sL[i] = cL(clamp(xs+i));
   // sR[j] = cR(clamp(xs + j - DC - 1 - dbase)): column i, local disparity dl -> j = i - dl + DC + 1
@@ -77,8 +76,10 @@ __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, cons
   const int ib = strip * TX; // staged index of my first hamming column
   // output cursor: element (y, xs+HW+ib, d_lo) of the first emitted row
   const int xo0 = xs + HW + ib;
-  uint16_t *prow = outC + ((size_t)y_begin * cols + xo0) * D + d_lo;
-  const size_t rowpitch = (size_t)cols * D;
+  // 32-bit byte offsets from the (block-uniform) image base: one volume is < 4 GB
+  uint32_t prow = (uint32_t)((((size_t)y_begin * cols + xo0) * D + d_lo) * 2);
+  const uint32_t rowpitch = (uint32_t)((size_t)cols * D * 2), colpitch = (uint32_t)D * 2;
+  char *const outB = reinterpret_cast<char *>(outC);
 
   const int nin = (y_end - y_begin) + BH - 1;
   gload(y_begin - HH);
@@ -142,7 +143,7 @@ __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, cons
           hs -= h[x];
         }
       } else {
-        uint16_t *dst = prow;
+        uint32_t dst = prow;
 #pragma unroll
         for (int x = 0; x < TX; ++x) {
           hs += h[x + BW - 1];
@@ -150,14 +151,15 @@ __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, cons
           ring_put(x, hs);
           hs -= h[x];
           if (!EDGE || xo0 + x < cols) {
-            if (even_d) {
-              *reinterpret_cast<uint32_t *>(dst) = vacc[x];
+            if (!ODD_D) {
+              *reinterpret_cast<uint32_t *>(outB + dst) = vacc[x];
             } else {
-              dst[0] = (uint16_t)(vacc[x] & 0xffffu);
-              if (d_lo + 1 < D) dst[1] = (uint16_t)(vacc[x] >> 16);
+              uint16_t *d16 = reinterpret_cast<uint16_t *>(outB + dst);
+              d16[0] = (uint16_t)(vacc[x] & 0xffffu);
+              if (d_lo + 1 < D) d16[1] = (uint16_t)(vacc[x] >> 16);
             }
           }
-          dst += D;
+          dst += colpitch;
           vacc[x] -= ring_get(x); // the row that leaves the window before the next input
         }
         prow += rowpitch;
@@ -186,10 +188,12 @@ cost_kernel(const uint32_t *__restrict__ cL, const uint32_t *__restrict__ cR,
   const uint32_t *imR = cR + (size_t)n * rows * cols;
   uint16_t *outC = C + (size_t)n * rows * cols * D;
   const bool edge = (xblk + 1) * (NS * TX) + BW / 2 > cols; // needs the replicate-border hold / x bound
-  if (edge)
-    cost_band<BW, BH, TX, NS, TD, true, PACK8>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR);
+  if (D & 1) // odd D (generic aggregation path only): 16-bit stores, keep one slow variant
+    cost_band<BW, BH, TX, NS, TD, true, PACK8, true>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR);
+  else if (edge)
+    cost_band<BW, BH, TX, NS, TD, true, PACK8, false>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR);
   else
-    cost_band<BW, BH, TX, NS, TD, false, PACK8>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR);
+    cost_band<BW, BH, TX, NS, TD, false, PACK8, false>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR);
 }
 
 // Any block size: direct evaluation (bw*bh POPC per output).  Only used for block sizes that have
