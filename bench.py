@@ -261,12 +261,16 @@ def run_ours(args, rank, world, local):
     kernel_bytes = {"cost": 8 * s * batch + V, "aggr_left": 2 * V, "aggr_down": 2 * V, "aggr_up": 4 * V, "aggr_right_wta": 2 * V + 6 * s * batch}
     st_ms = {k: v for k, v in stages.items() if k != "frames"}
     dom = max((k for k in kernel_bytes if k in st_ms), key=lambda k: st_ms[k], default=None)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_c1.json")
+    if args.workload == "C1" and batch == 1 and os.path.exists(tpath):  # measured DRAM bytes per launch from the committed ncu capture
+        traffic = json.load(open(tpath))["dram_bytes_per_launch"]
     roofline = None
     if dom:
         ach = kernel_bytes[dom] / (st_ms[dom] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": {"cost": "cost_kernel", "aggr_left": "aggr_kernel<MODE 0> (right->left)", "aggr_down": "aggr_kernel<MODE 0> (top->bottom)",
                                                "aggr_up": "aggr_kernel<MODE 1> (bottom->top + L1 + L2)", "aggr_right_wta": "aggr_wta_kernel (left->right + blend + WTA)"}[dom],
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": (traffic or {}).get(dom),
                     "algorithmic_bytes_per_launch": int(kernel_bytes[dom]), "avg_launch_ms": st_ms[dom], "peak_source": peak_src,
                     "per_kernel_gbs": {k: kernel_bytes[k] / (st_ms[k] * 1e-3) / 1e9 for k in kernel_bytes if k in st_ms}}
     alg = configs.algorithmic_bytes(prm, rgba_input=True, bbox=bbox_t, point_cloud=pc) * batch
