@@ -114,6 +114,7 @@ def dist_setup(n_gpus):
     if world > 1:
         import torch.distributed as dist
 
+        os.environ["NCCL_DEBUG"] = os.environ.get("SSB_NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return rank, world, local
 
