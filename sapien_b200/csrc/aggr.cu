@@ -31,6 +31,8 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace ssb {
 
 struct AggrArgs {
@@ -47,6 +49,21 @@ struct AggrArgs {
   int uniq;
   int nsm; // SM count: blocks b and b + nsm land on the same SM in the first wave
 };
+
+// ---- optional per-block timeline (debug/profiling aid, tools/trace_aggr.py): when a buffer is
+// registered, lane 0 of every path warp records {start ns, end ns, SM id, start clock} --------------
+__device__ unsigned long long *g_trace = nullptr;
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned smid() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %smid;" : "=r"(r));
+  return r;
+}
+constexpr int TRACE_STRIDE = 8192; // records per kernel slot
 
 // ---- mbarrier + bulk-copy (TMA 1-D) primitives -------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -217,7 +234,7 @@ __global__ void __launch_bounds__(128) aggr_kernel(const AggrArgs a) {
   if (path >= (long)a.N * (a.vertical ? a.cols : a.rows)) return; // warps are independent: no block barrier
   const PathGeom pg = path_geom(a, path);
   const int steps = pg.steps;
-  const int D = a.D;
+  const int D = PARTIAL ? a.D : 64 * NR; // whole lanes: D is a compile-time constant, ring offsets become immediates
   const int PIECE = D * 2;
   const AggrSmem lay = aggr_smem<MODE, K, NCH>(D);
   unsigned char *wsm = smem_raw + (size_t)warp * lay.total;
@@ -245,6 +262,9 @@ __global__ void __launch_bounds__(128) aggr_kernel(const AggrArgs a) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncwarp();
+  unsigned long long *const tr = g_trace;
+  const int tslot = (MODE == 1 ? 2 : a.vertical) * TRACE_STRIDE + (int)(path % TRACE_STRIDE);
+  if (tr && lane == 0) { tr[4 * tslot] = gtimer(); tr[4 * tslot + 2] = smid(); }
   const int nchunks = (steps + K - 1) / K;
   for (int ci = 0; ci < NCH - 1 && ci < nchunks; ++ci) pr.issue(ci);
 
@@ -307,6 +327,7 @@ __global__ void __launch_bounds__(128) aggr_kernel(const AggrArgs a) {
     }
     if (++slot == NCH) { slot = 0; parity ^= 1; }
   }
+  if (tr && lane == 0) tr[4 * tslot + 1] = gtimer();
 }
 
 // ---- MODE 2: left->right path + blend + winner-takes-all, two warps per image row ---------------
@@ -316,23 +337,33 @@ __global__ void __launch_bounds__(128) aggr_kernel(const AggrArgs a) {
 // Hand-over through two full/empty mbarrier pairs, so the serial SGM chain never waits for the
 // winner-takes-all arithmetic.
 template <int NR, bool PARTIAL, bool DBG, int K, int NCH>
-__global__ void __launch_bounds__(128) aggr_wta_kernel(const AggrArgs a) {
+__global__ void __launch_bounds__(320) aggr_wta_kernel(const AggrArgs a) {
   constexpr int DPL = 2 * NR;
   constexpr int NS = 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  // Warp slots map to the 4 schedulers of an SM by slot % 4 and a 2-warp block takes two adjacent
-  // slots, so a fixed role order would put every producer of an SM on the same two schedulers.
-  // Blocks b, b+nsm, b+2*nsm share an SM (round-robin first wave): alternate the order with b / nsm.
-  const int role = (warp ^ (blockIdx.x / a.nsm)) & 1;
+  // Placement: ONE block per SM carries up to 5 rows (5 producer + 5 consumer warps), and warp w of
+  // a block issues from scheduler w % 4.  The serial SGM chain of a producer is what bounds the
+  // kernel, and it stretches when it shares a scheduler with other busy warps (measured with the
+  // per-path timeline, tools/trace_aggr.py: 2-warp blocks scattered by the hardware left one row per
+  // SM ~35 % slower than the rest).  So the roles are pinned: producers on warps 0..3 (one per
+  // scheduler) and, for the fifth row, warp 6 (the scheduler that otherwise hosts only 2 warps);
+  // consumers fill the remaining slots.
   const int ppb = blockDim.x >> 6; // paths (rows) per block
-  const long path = (long)blockIdx.x * ppb + (warp >> 1);
+  int role, pi;
+  if (ppb == 5) {
+    const unsigned code = (unsigned)((0xcba4983210ull >> (4 * warp)) & 0xfull); // nibble = role << 3 | row-in-block, for warps 9..0: C4 C3 C2 P4 C1 C0 P3 P2 P1 P0
+    role = (int)(code >> 3); pi = (int)(code & 7u);
+  } else {
+    role = warp >= ppb; pi = role ? warp - ppb : warp;
+  }
+  const long path = (long)blockIdx.x * ppb + pi;
   const bool valid = path < (long)a.N * a.rows;
-  const int D = a.D;
+  const int D = PARTIAL ? a.D : 64 * NR; // whole lanes: D is a compile-time constant, ring offsets become immediates
   const int PIECE = D * 2;
   const AggrSmem lay = aggr_smem<2, K, NCH>(D);
-  unsigned char *wsm = smem_raw + (size_t)(warp >> 1) * lay.total;
+  unsigned char *wsm = smem_raw + (size_t)pi * lay.total;
   const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(wsm);
   const uint32_t barFull = bar0 + 8 * NCH, barEmpty = barFull + 8 * WTA_TILES;
   if (role == 0 && lane == 0) {
@@ -351,6 +382,9 @@ __global__ void __launch_bounds__(128) aggr_wta_kernel(const AggrArgs a) {
   const int TP = PIECE + 16; // tile row pitch: the per-pixel phase's lanes hit distinct banks
   unsigned char *tile = wsm + lay.tile;
   const int ntiles = (steps + 31) / 32;
+  unsigned long long *const tr = g_trace;
+  const int tslot = 3 * TRACE_STRIDE + (int)(path % TRACE_STRIDE);
+  if (tr && lane == 0 && role == 0) { tr[4 * tslot] = gtimer(); tr[4 * tslot + 2] = smid(); }
 
   if (role == 0) {
     // =========================== producer: SGM path + blend ===================================
@@ -427,6 +461,7 @@ __global__ void __launch_bounds__(128) aggr_wta_kernel(const AggrArgs a) {
       }
       if (++slot == NCH) { slot = 0; parity ^= 1; }
     }
+    if (tr && lane == 0) tr[4 * tslot + 1] = gtimer();
     return;
   }
 
@@ -566,6 +601,7 @@ __global__ void __launch_bounds__(128) aggr_wta_kernel(const AggrArgs a) {
       if (d < D - 1 && xp >= 0) a.dispR[rowpix + xp] = (uint16_t)(T[k] & 0xffffu);
     }
   }
+  if (tr && lane == 0) tr[4 * tslot + 3] = gtimer();
 }
 
 template <int NR> struct AggrCfg {
@@ -574,17 +610,24 @@ template <int NR> struct AggrCfg {
   template <int MODE> static constexpr int NCH() { return MODE == 0 ? 4 : 3; }
 };
 
-template <int NR, int MODE, bool PARTIAL, bool DBG>
+template <int NR, int MODE, bool PARTIAL, bool DBG, int NCHO = 0>
 static cudaError_t launch_one(const AggrArgs &a, cudaStream_t st) {
   constexpr int K = AggrCfg<NR>::template K<MODE>();
-  constexpr int NCH = AggrCfg<NR>::template NCH<MODE>();
-  const size_t smem = (size_t)aggr_smem<MODE, K, NCH>(a.D).total; // one path per block
+  constexpr int NCH = NCHO ? NCHO : AggrCfg<NR>::template NCH<MODE>();
+  const size_t smem = (size_t)aggr_smem<MODE, K, NCH>(a.D).total; // per path
   const long npaths = (long)a.N * (a.vertical ? a.cols : a.rows);
   cudaError_t e;
   if constexpr (MODE == 2) {
     auto k = aggr_wta_kernel<NR, PARTIAL, DBG, K, NCH>;
-    if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    k<<<(unsigned)npaths, 64, smem, st>>>(a);
+    // rows per block: enough for one resident wave with one block per SM when shared memory allows (<= 5)
+    long ppb = (npaths + a.nsm - 1) / a.nsm;
+    const long fit = (long)((227 * 1024) / smem);
+    if (ppb > 5) ppb = 5;
+    if (ppb > fit) ppb = fit;
+    if (ppb < 1) ppb = 1;
+    const size_t bsmem = smem * (size_t)ppb;
+    if (bsmem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem)) != cudaSuccess) return e;
+    k<<<(unsigned)((npaths + ppb - 1) / ppb), (unsigned)(64 * ppb), bsmem, st>>>(a);
   } else {
     auto k = aggr_kernel<NR, MODE, PARTIAL, DBG, K, NCH>;
     if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
@@ -595,13 +638,13 @@ static cudaError_t launch_one(const AggrArgs &a, cudaStream_t st) {
 
 static int nr_for(int D) { return D <= 64 ? 1 : D <= 128 ? 2 : D <= 256 ? 4 : D <= 512 ? 8 : 16; }
 
-template <int MODE> static cudaError_t dispatch(const AggrArgs &a, cudaStream_t st) {
+template <int MODE, int NCHO = 0> static cudaError_t dispatch(const AggrArgs &a, cudaStream_t st) {
   const int nr = nr_for(a.D);
   const bool partial = a.D != 64 * nr;
   const bool dbg = MODE != 0 && a.dbg0 != nullptr;
 #define SSB_CASE(NRV)                                                                             \
   case NRV:                                                                                       \
-    if (MODE == 0) return partial ? launch_one<NRV, MODE, true, false>(a, st) : launch_one<NRV, MODE, false, false>(a, st); \
+    if (MODE == 0) return partial ? launch_one<NRV, MODE, true, false, NCHO>(a, st) : launch_one<NRV, MODE, false, false, NCHO>(a, st); \
     if (dbg) return partial ? launch_one<NRV, MODE, true, true>(a, st) : launch_one<NRV, MODE, false, true>(a, st);  \
     return partial ? launch_one<NRV, MODE, true, false>(a, st) : launch_one<NRV, MODE, false, false>(a, st);
   switch (nr) {
@@ -610,6 +653,13 @@ template <int MODE> static cudaError_t dispatch(const AggrArgs &a, cudaStream_t 
 #undef SSB_CASE
   return cudaErrorInvalidValue;
 }
+
+} // namespace ssb
+// debug hook (not part of include/ss_b200.h): register a device buffer of 4 * 4 * TRACE_STRIDE u64
+extern "C" int ssb_debug_set_aggr_trace(void *device_buffer) {
+  return (int)cudaMemcpyToSymbol(ssb::g_trace, &device_buffer, sizeof(device_buffer));
+}
+namespace ssb {
 
 bool aggr_fast_supported(int D, int cmax, int P1, int P2) {
   if (D < 8 || D > 1024) return false;
@@ -640,17 +690,31 @@ cudaError_t launch_aggr_wta(const AggrBuffers &b, int N, int rows, int cols, int
     a.nsm = nsm;
   }
   cudaError_t err;
-  (void)s_aux; (void)ev;
-  // right->left, then top->bottom.  Both passes are HBM-bound on their own (measured 86 us + 85 us
-  // alone vs 177 us when forked onto two streams), so they simply run back to back.
+  // right->left and top->bottom are independent.  Alone, each leaves HBM bandwidth unused (the
+  // horizontal pass is bound by its 1280-step serial chain, 92 us + 92 us back to back); forked onto
+  // two streams with 2-slot rings -- so that the blocks of BOTH kernels are resident together --
+  // the pair takes 162 us.  SSB_AGGR_FORK=0 runs them back to back (4-slot rings), =1 forks with
+  // 3-slot rings (measured: no gain, the blocks do not all fit).
+  static const int fork = getenv("SSB_AGGR_FORK") ? atoi(getenv("SSB_AGGR_FORK")) : 2;
   AggrArgs h = a;
   h.vertical = 0; h.reverse = 1; h.out = b.L1;
-  if ((err = dispatch<0>(h, stream)) != cudaSuccess) return err;
-  mark("aggr_left");
   AggrArgs v = a;
   v.vertical = 1; v.reverse = 0; v.out = b.L2;
-  if ((err = dispatch<0>(v, stream)) != cudaSuccess) return err;
-  mark("aggr_down");
+  if (fork) {
+    if ((err = cudaEventRecord(ev[0], stream)) != cudaSuccess) return err;
+    if ((err = cudaStreamWaitEvent(s_aux, ev[0], 0)) != cudaSuccess) return err;
+    if ((err = (fork == 2 ? dispatch<0, 2>(v, s_aux) : dispatch<0, 3>(v, s_aux))) != cudaSuccess) return err;
+    if ((err = (fork == 2 ? dispatch<0, 2>(h, stream) : dispatch<0, 3>(h, stream))) != cudaSuccess) return err;
+    if ((err = cudaEventRecord(ev[1], s_aux)) != cudaSuccess) return err;
+    if ((err = cudaStreamWaitEvent(stream, ev[1], 0)) != cudaSuccess) return err;
+    mark("aggr_left");
+    mark("aggr_down");
+  } else {
+    if ((err = dispatch<0>(h, stream)) != cudaSuccess) return err;
+    mark("aggr_left");
+    if ((err = dispatch<0>(v, stream)) != cudaSuccess) return err;
+    mark("aggr_down");
+  }
   // bottom->top, accumulating L1+L2+L3
   AggrArgs u = a;
   u.vertical = 1; u.reverse = 1; u.aux0 = b.L1; u.aux1 = b.L2; u.out = b.S3; u.dbg0 = b.dbgL3;

@@ -20,11 +20,13 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace ssb {
 
-template <int BW, int BH, int TX, int NS, int TD, bool EDGE, bool PACK8, bool ODD_D>
+template <int BW, int BH, int TX, int NS, int TD, bool EDGE, bool PACK8, bool ODD_D, int DT>
 __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, const uint32_t *__restrict__ imR,
-                                          uint16_t *__restrict__ outC, int rows, int cols, int D, int dbase,
+                                          uint16_t *__restrict__ outC, int rows, int cols, int Drt, int dbase,
                                           int xblk, int y_begin, int y_end, uint32_t *ring,
                                           uint32_t *sLb, uint32_t *sRb) {
   constexpr int HW = BW / 2, HH = BH / 2;
@@ -38,6 +40,7 @@ __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, cons
   constexpr int NLD = (NRC + nthreads - 1) / nthreads;
   constexpr int SLS = (NXW + 3) & ~3, SRS = (NRC + 3) & ~3; // row strides keep vector loads aligned
 
+  const int D = DT ? DT : Drt; // DT != 0: compile-time D, the column offsets of the stores become immediates
   const int td = threadIdx.x; // disparity pair inside the chunk
   const int strip = threadIdx.y;
   const int tid = strip * TD + td;
@@ -76,10 +79,9 @@ __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, cons
   const int ib = strip * TX; // staged index of my first hamming column
   // output cursor: element (y, xs+HW+ib, d_lo) of the first emitted row
   const int xo0 = xs + HW + ib;
-  // 32-bit byte offsets from the (block-uniform) image base: one volume is < 4 GB
-  uint32_t prow = (uint32_t)((((size_t)y_begin * cols + xo0) * D + d_lo) * 2);
-  const uint32_t rowpitch = (uint32_t)((size_t)cols * D * 2), colpitch = (uint32_t)D * 2;
-  char *const outB = reinterpret_cast<char *>(outC);
+  char *prow = reinterpret_cast<char *>(outC) + (((size_t)y_begin * cols + xo0) * D + d_lo) * 2;
+  const size_t rowpitch = (size_t)cols * D * 2;
+  const uint32_t colpitch = (uint32_t)D * 2;
 
   const int nin = (y_end - y_begin) + BH - 1;
   gload(y_begin - HH);
@@ -109,7 +111,8 @@ __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, cons
 #pragma unroll
       for (int i = 0; i < NH; ++i) {
         // code for d_lo+1 at this column == code for d_lo one column to the left
-        const uint32_t hv = (uint32_t)__popc(av[i] ^ rv[i + 1]) + ((uint32_t)__popc(av[i] ^ rv[i]) << 16);
+        uint32_t hv; // popc(d_lo) | popc(d_lo+1) << 16 as ONE multiply-add (fma pipe; the alu pipe is the busy one)
+        asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(hv) : "r"(__popc(av[i] ^ rv[i])), "r"(__popc(av[i] ^ rv[i + 1])));
         if (EDGE) { if (ib + i <= imax) hcur = hv; h[i] = hcur; }
         else h[i] = hv;
       }
@@ -143,7 +146,6 @@ __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, cons
           hs -= h[x];
         }
       } else {
-        uint32_t dst = prow;
 #pragma unroll
         for (int x = 0; x < TX; ++x) {
           hs += h[x + BW - 1];
@@ -151,15 +153,15 @@ __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, cons
           ring_put(x, hs);
           hs -= h[x];
           if (!EDGE || xo0 + x < cols) {
+            char *dst = prow + (uint32_t)x * colpitch;
             if (!ODD_D) {
-              *reinterpret_cast<uint32_t *>(outB + dst) = vacc[x];
+              *reinterpret_cast<uint32_t *>(dst) = vacc[x];
             } else {
-              uint16_t *d16 = reinterpret_cast<uint16_t *>(outB + dst);
+              uint16_t *d16 = reinterpret_cast<uint16_t *>(dst);
               d16[0] = (uint16_t)(vacc[x] & 0xffffu);
               if (d_lo + 1 < D) d16[1] = (uint16_t)(vacc[x] >> 16);
             }
           }
-          dst += colpitch;
           vacc[x] -= ring_get(x); // the row that leaves the window before the next input
         }
         prow += rowpitch;
@@ -171,7 +173,7 @@ __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, cons
   }
 }
 
-template <int BW, int BH, int TX, int NS, int TD, bool PACK8>
+template <int BW, int BH, int TX, int NS, int TD, bool PACK8, int DT>
 __global__ void __launch_bounds__(TD *NS)
 cost_kernel(const uint32_t *__restrict__ cL, const uint32_t *__restrict__ cR,
             uint16_t *__restrict__ C, int rows, int cols, int D, int nchunks, int ry) {
@@ -188,12 +190,12 @@ cost_kernel(const uint32_t *__restrict__ cL, const uint32_t *__restrict__ cR,
   const uint32_t *imR = cR + (size_t)n * rows * cols;
   uint16_t *outC = C + (size_t)n * rows * cols * D;
   const bool edge = (xblk + 1) * (NS * TX) + BW / 2 > cols; // needs the replicate-border hold / x bound
-  if (D & 1) // odd D (generic aggregation path only): 16-bit stores, keep one slow variant
-    cost_band<BW, BH, TX, NS, TD, true, PACK8, true>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR);
+  if (DT == 0 && (D & 1)) // odd D (generic aggregation path only): 16-bit stores, keep one slow variant
+    cost_band<BW, BH, TX, NS, TD, true, PACK8, true, 0>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR);
   else if (edge)
-    cost_band<BW, BH, TX, NS, TD, true, PACK8, false>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR);
+    cost_band<BW, BH, TX, NS, TD, true, PACK8, false, DT>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR);
   else
-    cost_band<BW, BH, TX, NS, TD, false, PACK8, false>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR);
+    cost_band<BW, BH, TX, NS, TD, false, PACK8, false, DT>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR);
 }
 
 // Any block size: direct evaluation (bw*bh POPC per output).  Only used for block sizes that have
@@ -225,10 +227,10 @@ __global__ void cost_generic_kernel(const uint32_t *__restrict__ cL, const uint3
 
 static int g_sm_count = 0;
 
-template <int BW, int BH, int TX, int NS, int TD, bool PACK8>
+template <int BW, int BH, int TX, int NS, int TD, bool PACK8, int DT = 0>
 static cudaError_t launch_cfg(const uint32_t *cL, const uint32_t *cR, uint16_t *C, int N, int rows,
                               int cols, int D, cudaStream_t st) {
-  auto k = cost_kernel<BW, BH, TX, NS, TD, PACK8>;
+  auto k = cost_kernel<BW, BH, TX, NS, TD, PACK8, DT>;
   const size_t smem = (size_t)BH * NS * TX * TD * sizeof(uint32_t) / (PACK8 ? 2 : 1);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -262,6 +264,15 @@ static cudaError_t launch_fast(const uint32_t *cL, const uint32_t *cR, uint16_t 
   constexpr int TX = 16;
   // a BW-wide Hamming sum fits one byte: half-size ring (BH == 1 reads back the word it is writing)
   const bool pack8 = BH > 1 && BW * bits <= 255;
+  if constexpr (BW == 7 && BH == 7) if (pack8) { // the stock block size: compile-time D for the usual disparity ranges
+    if (D == 64) return launch_cfg<BW, BH, TX, 4, 32, true, 64>(cL, cR, C, N, rows, cols, D, st);
+    if (D == 96) return launch_cfg<BW, BH, TX, 2, 64, true, 96>(cL, cR, C, N, rows, cols, D, st);
+    static const int wide = getenv("SSB_COST_TX") ? atoi(getenv("SSB_COST_TX")) : 0; // experiment: wider strips
+    if (D == 128 && wide == 32) return launch_cfg<BW, BH, 32, 2, 64, true, 128>(cL, cR, C, N, rows, cols, D, st);
+    if (D == 128 && wide == 24) return launch_cfg<BW, BH, 24, 2, 64, true, 128>(cL, cR, C, N, rows, cols, D, st);
+    if (D == 128) return launch_cfg<BW, BH, TX, 2, 64, true, 128>(cL, cR, C, N, rows, cols, D, st);
+    if (D == 256) return launch_cfg<BW, BH, TX, 2, 64, true, 256>(cL, cR, C, N, rows, cols, D, st);
+  }
   if (D <= 64)
     return pack8 ? launch_cfg<BW, BH, TX, 4, 32, true>(cL, cR, C, N, rows, cols, D, st)
                  : launch_cfg<BW, BH, TX, 4, 32, false>(cL, cR, C, N, rows, cols, D, st);
