@@ -24,59 +24,80 @@
 
 namespace ssb {
 
-template <int BW, int BH, int TX, int NS, int TD, bool EDGE, bool PACK8, bool ODD_D, int DT>
+// optional per-block timeline (debug aid, tools/trace_aggr.py): {start ns, end ns, SM id} per block
+__device__ unsigned long long *g_cost_trace = nullptr;
+__device__ __forceinline__ unsigned long long cost_gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+constexpr int CSTAGES = 4; // census rows in flight per warp (cp.async ring)
+template <int BW, int TX> struct CostStage { // per-warp staging buffers (words), CSTAGES deep
+  static constexpr int NH = TX + BW - 1;
+  static constexpr int SLS = (NH + 3) & ~3;
+  static constexpr int SRS = (NH + 64 + 2 + 3) & ~3;
+};
+
+template <int BW, int BH, int TX, int NS, int TD, bool EDGE, bool PACK8, bool ODD_D, int DT, int EXP = 0>
 __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, const uint32_t *__restrict__ imR,
                                           uint16_t *__restrict__ outC, int rows, int cols, int Drt, int dbase,
                                           int xblk, int y_begin, int y_end, uint32_t *ring,
                                           uint32_t *sLb, uint32_t *sRb) {
   constexpr int HW = BW / 2, HH = BH / 2;
   constexpr int NH = TX + BW - 1;       // hamming columns per strip
-  constexpr int NXW = NS * TX + BW - 1; // left census codes staged per block
-  constexpr int DC = 2 * TD;            // disparities per chunk
-  constexpr int NRC = NXW + DC + 1;     // right census codes staged per block
+  constexpr int DCW = 64;               // disparities per warp (32 lanes x one pair)
+  constexpr int NRC = NH + DCW + 1;     // right census codes staged per warp
   constexpr int SLOT = NS * TX * TD / (PACK8 ? 2 : 1); // ring words per input row
   constexpr int XW = PACK8 ? TX / 2 : TX;              // ring words per thread and row
-  constexpr int nthreads = TD * NS;
-  constexpr int NLD = (NRC + nthreads - 1) / nthreads;
-  constexpr int SLS = (NXW + 3) & ~3, SRS = (NRC + 3) & ~3; // row strides keep vector loads aligned
+  constexpr int NLL = (NH + 31) / 32, NLR = (NRC + 31) / 32;
+  constexpr int SLS = CostStage<BW, TX>::SLS, SRS = CostStage<BW, TX>::SRS; // strides keep vector loads aligned
 
   const int D = DT ? DT : Drt; // DT != 0: compile-time D, the column offsets of the stores become immediates
   const int td = threadIdx.x; // disparity pair inside the chunk
   const int strip = threadIdx.y;
-  const int tid = strip * TD + td;
+  const int lane = td & 31;
+  const int wq = td >> 5;               // warp inside the strip
   const int d_lo = dbase + 2 * td;      // my disparities: d_lo, d_lo+1
-  const int xs = xblk * (NS * TX) - HW; // image column of staged index 0
-  const int imax = cols - 1 - xs;       // staged index of the last image column (replicate border)
+  const int dbw = dbase + DCW * wq;     // first disparity of my warp
+  const int xs = xblk * (NS * TX) - HW; // image column of block index 0
+  const int ib = strip * TX;            // block index of my first hamming column
+  const int imax = cols - 1 - xs;       // block index of the last image column (replicate border)
   const bool live = d_lo < D;
+  if (dbw >= D) return;                 // whole warp beyond D: warps are independent (no block barrier)
 
-  // column indices this thread stages (row-independent).  sL[i] = cL(clamp(xs+i));
-  // sR[j] = cR(clamp(xs + j - DC - 1 - dbase)): column i, local disparity dl -> j = i - dl + DC + 1
-  const int colL = min(max(xs + tid, 0), cols - 1);
-  int colR[NLD];
+  // Every WARP stages the census codes of its own strip and disparity range (no __syncthreads in
+  // the row loop, so the warps of an SM drift apart and POPC bursts overlap with the other warps'
+  // sliding sums).  sL[i] = cL(clamp(xs+ib+i));  sR[j] = cR(clamp(xs+ib + j - DCW - 1 - dbw)):
+  // column i, lane l (disparity dbw + 2l) -> j = i - 2l + DCW + 1
+  int colL[NLL], colR[NLR];
 #pragma unroll
-  for (int k = 0; k < NLD; ++k) colR[k] = min(max(xs + tid + k * nthreads - DC - 1 - dbase, 0), cols - 1);
-  uint32_t vL = 0, vR[NLD];
-  auto gload = [&](int yin) {
+  for (int k = 0; k < NLL; ++k) colL[k] = min(max(xs + ib + lane + 32 * k, 0), cols - 1);
+#pragma unroll
+  for (int k = 0; k < NLR; ++k) colR[k] = min(max(xs + ib + lane + 32 * k - DCW - 1 - dbw, 0), cols - 1);
+  // rows are fetched global -> shared by cp.async, CSTAGES-1 rows ahead (one commit group per row):
+  // the row loop never waits for an L2 round trip (measured: with a one-row register prefetch a
+  // warp needed ~1800 cycles per row, most of it load latency)
+  const uint32_t sL_s = (uint32_t)__cvta_generic_to_shared(sLb), sR_s = (uint32_t)__cvta_generic_to_shared(sRb);
+  auto fetch = [&](int yin, int stage) {
     const int yc = min(max(yin, 0), rows - 1);
     const uint32_t *l = imL + (size_t)yc * cols;
     const uint32_t *r = imR + (size_t)yc * cols;
-    if (tid < NXW) vL = __ldg(l + colL);
 #pragma unroll
-    for (int k = 0; k < NLD; ++k)
-      if (tid + k * nthreads < NRC) vR[k] = __ldg(r + colR[k]);
-  };
-  auto sstore = [&](int buf) {
-    if (tid < NXW) sLb[buf * SLS + tid] = vL;
+    for (int k = 0; k < NLL; ++k)
+      if (lane + 32 * k < NH)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sL_s + 4u * (uint32_t)(stage * SLS + lane + 32 * k)), "l"(l + colL[k]) : "memory");
 #pragma unroll
-    for (int k = 0; k < NLD; ++k)
-      if (tid + k * nthreads < NRC) sRb[buf * SRS + tid + k * nthreads] = vR[k];
+    for (int k = 0; k < NLR; ++k)
+      if (lane + 32 * k < NRC)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sR_s + 4u * (uint32_t)(stage * SRS + lane + 32 * k)), "l"(r + colR[k]) : "memory");
   };
+  auto commit = [&]() { asm volatile("cp.async.commit_group;" ::: "memory"); };
 
   uint32_t vacc[TX];
 #pragma unroll
   for (int x = 0; x < TX; ++x) vacc[x] = 0;
   uint32_t *myring = ring + (size_t)strip * XW * TD + td;
-  const int ib = strip * TX; // staged index of my first hamming column
   // output cursor: element (y, xs+HW+ib, d_lo) of the first emitted row
   const int xo0 = xs + HW + ib;
   char *prow = reinterpret_cast<char *>(outC) + (((size_t)y_begin * cols + xo0) * D + d_lo) * 2;
@@ -84,17 +105,25 @@ __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, cons
   const uint32_t colpitch = (uint32_t)D * 2;
 
   const int nin = (y_end - y_begin) + BH - 1;
-  gload(y_begin - HH);
-  sstore(0);
-  __syncthreads();
+#pragma unroll
+  for (int s0 = 0; s0 < CSTAGES - 1; ++s0) {
+    if (s0 < nin) fetch(y_begin - HH + s0, s0);
+    commit();
+  }
   int wslot = 0; // ring slot written by this input row; the oldest row lives in slot wslot+1 (mod BH)
+  int buf = 0;   // staging slot of input row `it`
   for (int it = 0; it < nin; ++it) {
-    const int buf = it & 1;
-    if (it + 1 < nin) gload(y_begin - HH + it + 1);
+    asm volatile("cp.async.wait_group %0;" ::"n"(CSTAGES - 2) : "memory");
+    __syncwarp(); // row `it` is visible to the whole warp, and everybody is done with row it-1's slot
+    {
+      const int nb = buf == 0 ? CSTAGES - 1 : buf - 1; // slot of row it-1 == slot of row it+CSTAGES-1
+      if (it + CSTAGES - 1 < nin) fetch(y_begin - HH + it + CSTAGES - 1, nb);
+      commit();
+    }
     if (live) {
       // ---- Hamming pairs of my strip ---------------------------------------------------------
-      const uint32_t *pl = sLb + buf * SLS + ib;                     // 16-byte aligned (ib % 16 == 0)
-      const uint32_t *pr = sRb + buf * SRS + (DC + 1 - 2 * td) + ib; // pr[i] = cR(x_i - d_lo); pr-1 is 8-byte aligned
+      const uint32_t *pl = sLb + buf * SLS;                        // 16-byte aligned
+      const uint32_t *pr = sRb + buf * SRS + (DCW + 1 - 2 * lane); // pr[i] = cR(x_i - d_lo); pr-1 is 8-byte aligned
       uint32_t av[(NH + 3) & ~3], rv[(NH + 2) & ~1]; // rv[k] = pr[k-1]
 #pragma unroll
       for (int i4 = 0; i4 < NH; i4 += 4) {
@@ -112,7 +141,10 @@ __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, cons
       for (int i = 0; i < NH; ++i) {
         // code for d_lo+1 at this column == code for d_lo one column to the left
         uint32_t hv; // popc(d_lo) | popc(d_lo+1) << 16 as ONE multiply-add (fma pipe; the alu pipe is the busy one)
-        asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(hv) : "r"(__popc(av[i] ^ rv[i])), "r"(__popc(av[i] ^ rv[i + 1])));
+        if (EXP & 1) // timing experiment only (wrong results): no POPC
+          asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(hv) : "r"((av[i] ^ rv[i]) & 31u), "r"((av[i] ^ rv[i + 1]) & 31u));
+        else
+          asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(hv) : "r"(__popc(av[i] ^ rv[i])), "r"(__popc(av[i] ^ rv[i + 1])));
         if (EDGE) { if (ib + i <= imax) hcur = hv; h[i] = hcur; }
         else h[i] = hv;
       }
@@ -154,7 +186,9 @@ __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, cons
           hs -= h[x];
           if (!EDGE || xo0 + x < cols) {
             char *dst = prow + (uint32_t)x * colpitch;
-            if (!ODD_D) {
+            if (EXP & 2) { // timing experiment only: (almost) no stores
+              if (vacc[x] == 0xdeadbeefu) *reinterpret_cast<uint32_t *>(dst) = vacc[x];
+            } else if (!ODD_D) {
               *reinterpret_cast<uint32_t *>(dst) = vacc[x];
             } else {
               uint16_t *d16 = reinterpret_cast<uint16_t *>(dst);
@@ -168,18 +202,20 @@ __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, cons
       }
     }
     wslot = wslot + 1 == BH ? 0 : wslot + 1;
-    if (it + 1 < nin) sstore(buf ^ 1);
-    __syncthreads();
+    buf = buf + 1 == CSTAGES ? 0 : buf + 1;
   }
 }
 
-template <int BW, int BH, int TX, int NS, int TD, bool PACK8, int DT>
+template <int BW, int BH, int TX, int NS, int TD, bool PACK8, int DT, int EXP = 0>
 __global__ void __launch_bounds__(TD *NS)
 cost_kernel(const uint32_t *__restrict__ cL, const uint32_t *__restrict__ cR,
             uint16_t *__restrict__ C, int rows, int cols, int D, int nchunks, int ry) {
-  constexpr int NXW = NS * TX + BW - 1;
-  __shared__ __align__(16) uint32_t sL[2 * ((NXW + 3) & ~3)];
-  __shared__ __align__(16) uint32_t sR[2 * ((NXW + 2 * TD + 1 + 3) & ~3) + 4];
+  constexpr int NWARP = NS * TD / 32;
+  __shared__ __align__(16) uint32_t sLall[NWARP * CSTAGES * CostStage<BW, TX>::SLS];
+  __shared__ __align__(16) uint32_t sRall[NWARP * CSTAGES * CostStage<BW, TX>::SRS];
+  const int wib = (threadIdx.y * TD + threadIdx.x) >> 5; // warp in block
+  uint32_t *sL = sLall + wib * CSTAGES * CostStage<BW, TX>::SLS;
+  uint32_t *sR = sRall + wib * CSTAGES * CostStage<BW, TX>::SRS;
   extern __shared__ uint32_t ring[]; // [BH][NS][TX][TD], thread-private entries
   const int chunk = blockIdx.x % nchunks;
   const int xblk = blockIdx.x / nchunks;
@@ -190,12 +226,20 @@ cost_kernel(const uint32_t *__restrict__ cL, const uint32_t *__restrict__ cR,
   const uint32_t *imR = cR + (size_t)n * rows * cols;
   uint16_t *outC = C + (size_t)n * rows * cols * D;
   const bool edge = (xblk + 1) * (NS * TX) + BW / 2 > cols; // needs the replicate-border hold / x bound
+  unsigned long long *const tr = g_cost_trace;
+  const int tslot = (blockIdx.y * gridDim.x + blockIdx.x) % 8192;
+  if (tr && threadIdx.x == 0 && threadIdx.y == 0) {
+    unsigned sm;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+    tr[4 * tslot] = cost_gtimer(); tr[4 * tslot + 2] = sm;
+  }
   if (DT == 0 && (D & 1)) // odd D (generic aggregation path only): 16-bit stores, keep one slow variant
     cost_band<BW, BH, TX, NS, TD, true, PACK8, true, 0>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR);
   else if (edge)
-    cost_band<BW, BH, TX, NS, TD, true, PACK8, false, DT>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR);
+    cost_band<BW, BH, TX, NS, TD, true, PACK8, false, DT, EXP>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR);
   else
-    cost_band<BW, BH, TX, NS, TD, false, PACK8, false, DT>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR);
+    cost_band<BW, BH, TX, NS, TD, false, PACK8, false, DT, EXP>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR);
+  if (tr && threadIdx.x == 0 && threadIdx.y == 0) tr[4 * tslot + 1] = cost_gtimer();
 }
 
 // Any block size: direct evaluation (bw*bh POPC per output).  Only used for block sizes that have
@@ -227,10 +271,10 @@ __global__ void cost_generic_kernel(const uint32_t *__restrict__ cL, const uint3
 
 static int g_sm_count = 0;
 
-template <int BW, int BH, int TX, int NS, int TD, bool PACK8, int DT = 0>
+template <int BW, int BH, int TX, int NS, int TD, bool PACK8, int DT = 0, int EXP = 0>
 static cudaError_t launch_cfg(const uint32_t *cL, const uint32_t *cR, uint16_t *C, int N, int rows,
                               int cols, int D, cudaStream_t st) {
-  auto k = cost_kernel<BW, BH, TX, NS, TD, PACK8, DT>;
+  auto k = cost_kernel<BW, BH, TX, NS, TD, PACK8, DT, EXP>;
   const size_t smem = (size_t)BH * NS * TX * TD * sizeof(uint32_t) / (PACK8 ? 2 : 1);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -268,6 +312,10 @@ static cudaError_t launch_fast(const uint32_t *cL, const uint32_t *cR, uint16_t 
     if (D == 64) return launch_cfg<BW, BH, TX, 4, 32, true, 64>(cL, cR, C, N, rows, cols, D, st);
     if (D == 96) return launch_cfg<BW, BH, TX, 2, 64, true, 96>(cL, cR, C, N, rows, cols, D, st);
     static const int wide = getenv("SSB_COST_TX") ? atoi(getenv("SSB_COST_TX")) : 0; // experiment: wider strips
+    static const int exp_ = getenv("SSB_COST_EXP") ? atoi(getenv("SSB_COST_EXP")) : 0;
+    if (D == 128 && exp_ == 1) return launch_cfg<BW, BH, TX, 2, 64, true, 128, 1>(cL, cR, C, N, rows, cols, D, st);
+    if (D == 128 && exp_ == 2) return launch_cfg<BW, BH, TX, 2, 64, true, 128, 2>(cL, cR, C, N, rows, cols, D, st);
+    if (D == 128 && exp_ == 3) return launch_cfg<BW, BH, TX, 2, 64, true, 128, 3>(cL, cR, C, N, rows, cols, D, st);
     if (D == 128 && wide == 32) return launch_cfg<BW, BH, 32, 2, 64, true, 128>(cL, cR, C, N, rows, cols, D, st);
     if (D == 128 && wide == 24) return launch_cfg<BW, BH, 24, 2, 64, true, 128>(cL, cR, C, N, rows, cols, D, st);
     if (D == 128) return launch_cfg<BW, BH, TX, 2, 64, true, 128>(cL, cR, C, N, rows, cols, D, st);
@@ -279,6 +327,12 @@ static cudaError_t launch_fast(const uint32_t *cL, const uint32_t *cR, uint16_t 
   return pack8 ? launch_cfg<BW, BH, TX, 2, 64, true>(cL, cR, C, N, rows, cols, D, st)
                : launch_cfg<BW, BH, TX, 2, 64, false>(cL, cR, C, N, rows, cols, D, st);
 }
+
+} // namespace ssb
+extern "C" int ssb_debug_set_cost_trace(void *device_buffer) {
+  return (int)cudaMemcpyToSymbol(ssb::g_cost_trace, &device_buffer, sizeof(device_buffer));
+}
+namespace ssb {
 
 cudaError_t launch_cost(const uint32_t *cL, const uint32_t *cR, uint16_t *C, int N, int rows,
                         int cols, int D, int bw, int bh, int bits, cudaStream_t st) {
