@@ -259,7 +259,7 @@ def run_ours(args, rank, world, local):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     s = (prm.rows * prm.cols) if bbox_t is None else bbox_t[2] * bbox_t[3]
     V = 2 * s * prm.max_disp * batch
-    kernel_bytes = {"cost": 8 * s * batch + V, "aggr_left": 2 * V, "aggr_down": 2 * V, "aggr_up": 4 * V, "aggr_right_wta": 2 * V + 6 * s * batch}
+    kernel_bytes = {"cost": 8 * s * batch + V, "aggr_left": 2 * V, "aggr_down": 2 * V, "aggr_left_down": 4 * V, "aggr_up": 4 * V, "aggr_right_wta": 2 * V + 6 * s * batch}
     st_ms = {k: v for k, v in stages.items() if k != "frames"}
     dom = max((k for k in kernel_bytes if k in st_ms), key=lambda k: st_ms[k], default=None)
     traffic = None
@@ -270,6 +270,7 @@ def run_ours(args, rank, world, local):
     if dom:
         ach = kernel_bytes[dom] / (st_ms[dom] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": {"cost": "cost_kernel", "aggr_left": "aggr_kernel<MODE 0> (right->left)", "aggr_down": "aggr_kernel<MODE 0> (top->bottom)",
+                                               "aggr_left_down": "aggr_kernel<MODE 0> x2 (right->left || top->bottom, two streams)",
                                                "aggr_up": "aggr_kernel<MODE 1> (bottom->top + L1 + L2)", "aggr_right_wta": "aggr_wta_kernel (left->right + blend + WTA)"}[dom],
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": (traffic or {}).get(dom),
                     "algorithmic_bytes_per_launch": int(kernel_bytes[dom]), "avg_launch_ms": st_ms[dom], "peak_source": peak_src,

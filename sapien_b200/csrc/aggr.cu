@@ -707,8 +707,7 @@ cudaError_t launch_aggr_wta(const AggrBuffers &b, int N, int rows, int cols, int
     if ((err = (fork == 2 ? dispatch<0, 2>(h, stream) : dispatch<0, 3>(h, stream))) != cudaSuccess) return err;
     if ((err = cudaEventRecord(ev[1], s_aux)) != cudaSuccess) return err;
     if ((err = cudaStreamWaitEvent(stream, ev[1], 0)) != cudaSuccess) return err;
-    mark("aggr_left");
-    mark("aggr_down");
+    mark("aggr_left_down"); // one interval: the two kernels run concurrently
   } else {
     if ((err = dispatch<0>(h, stream)) != cudaSuccess) return err;
     mark("aggr_left");

@@ -60,6 +60,39 @@ template <int OP> void run(uint32_t *out, long long *cyc) {
   printf("%-16s chain step %.1f cyc | %.1f thread-ops/clk/SM (16 warps/SM) | %.1f (4 warps/SM)\n", names[OP], lat, per_sm_clk, per_sm_clk1);
 }
 
+// POPC mixed with shared-memory loads / stores: do the xu pipe and the lsu share a dispatch port?
+template <int NPOPC, int NLDS, int NSTS, int NALU> __global__ void mix(uint32_t *out, uint32_t k, int iters, long long *cyc) {
+  __shared__ uint32_t sm[32 * 16 * 9];
+  uint32_t p[8], l[8], a[8];
+  uint32_t *mine = sm + (threadIdx.x >> 5) * 32 * 9 + (threadIdx.x & 31);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { p[i] = threadIdx.x + i + k; l[i] = 0; a[i] = i; mine[i * 32] = i; }
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < NPOPC) p[i] = __popc(p[i]) + k;
+      if (i < NLDS) l[i] += *(volatile uint32_t *)(mine + i * 32);
+      if (i < NSTS) *(volatile uint32_t *)(mine + i * 32) = a[i];
+      if (i < NALU) a[i] = __byte_perm(a[i], k, 0x1230);
+    }
+  }
+  const long long t1 = clock64();
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s ^= p[i] ^ l[i] ^ a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+template <int NPOPC, int NLDS, int NSTS, int NALU> void runmix(uint32_t *out, long long *cyc) {
+  const int iters = 2048;
+  long long h = 0;
+  mix<NPOPC, NLDS, NSTS, NALU><<<148, 512>>>(out, 3, iters, cyc);
+  cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+  printf("mix popc=%d lds=%d sts=%d alu=%d per iteration: %.1f cycles/iteration/SMSP-warp-set (16 warps/SM => 4 warps per SMSP)\n", NPOPC, NLDS, NSTS, NALU, (double)h / iters);
+}
+
 int main() {
   uint32_t *out;
   long long *cyc;
@@ -76,6 +109,16 @@ int main() {
   run<VMIN3>(out, cyc);
   run<REDUX>(out, cyc);
   run<SHFL>(out, cyc);
+  runmix<8, 0, 0, 0>(out, cyc);
+  runmix<0, 8, 0, 0>(out, cyc);
+  runmix<0, 0, 8, 0>(out, cyc);
+  runmix<0, 0, 0, 8>(out, cyc);
+  runmix<8, 8, 0, 0>(out, cyc);
+  runmix<8, 0, 8, 0>(out, cyc);
+  runmix<8, 0, 0, 8>(out, cyc);
+  runmix<8, 8, 8, 8>(out, cyc);
+  runmix<4, 8, 8, 8>(out, cyc);
+  runmix<2, 8, 8, 8>(out, cyc);
   cudaError_t e = cudaDeviceSynchronize();
   printf("status: %s\n", cudaGetErrorString(e));
   return e != cudaSuccess;
