@@ -207,11 +207,15 @@ template <int I, int J> struct CensusBits {
   }
 };
 
-template <bool RGBA>
-__global__ void __launch_bounds__(F7_NT, 4) front7_kernel(const FrontParams p) {
-  __shared__ __align__(16) uint32_t win[2][F7_WH][F7_WB / 4];
+// One block = one tile of ONE image (blockIdx.z = 2 * env + image): twice the blocks and half the
+// dependent load rounds per block of a both-images block (the kernel is bound by the latency of
+// the map -> texel gather, not by bandwidth).
+template <bool RGBA, int MINB>
+__global__ void __launch_bounds__(F7_NT, MINB) front7_kernel(const FrontParams p) {
+  __shared__ __align__(16) uint32_t win[1][F7_WH][F7_WB / 4];
   const int tid = threadIdx.x;
-  const int n = blockIdx.z;
+  const int n = blockIdx.z >> 1;
+  const int img = blockIdx.z & 1;
   const int X0 = blockIdx.x * F7_TW, Y0 = blockIdx.y * F7_TH;
   if (p.canvas) { // grid-stride fill of the registration canvas (initRgbDepth, camera.cu:170-177)
     const size_t nthr = (size_t)gridDim.x * gridDim.y * gridDim.z * F7_NT;
@@ -224,17 +228,15 @@ __global__ void __launch_bounds__(F7_NT, 4) front7_kernel(const FrontParams p) {
   const Src sl{p.left_u8, p.left_rgba, p.mapLx, p.mapLy};
   const Src sr{p.right_u8, p.right_rgba, p.mapRx, p.mapRy};
   uint8_t *b0 = reinterpret_cast<uint8_t *>(&win[0][0][0]);
-  uint8_t *b1 = reinterpret_cast<uint8_t *>(&win[1][0][0]);
   constexpr int NEL = F7_WB * F7_WH;
   constexpr int NRND = (NEL + F7_NT - 1) / F7_NT; // texels per thread and image
   constexpr int HALF = (NRND + 1) / 2;
   // Branch-free staging in three straight-line phases (map loads -> texel loads -> convert/store) so
   // that all loads of a phase are in flight together; out-of-image texels are loaded from a clamped
   // address and replaced by the zero padding of csct.cu:40-42 afterwards.
-#pragma unroll
-  for (int img = 0; img < 2; ++img) {
+  {
     const Src &s = img ? sr : sl;
-    uint8_t *bdst = img ? b1 : b0;
+    uint8_t *bdst = b0;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       int fx[HALF], fy[HALF];
@@ -283,15 +285,14 @@ __global__ void __launch_bounds__(F7_NT, 4) front7_kernel(const FrontParams p) {
   const int tx = tid & 15, ty = tid >> 4; // 16 x 8 threads, 4 pixels x 4 rows each
   const int x0 = X0 + 4 * tx;
   if (x0 >= p.cols) return;
-#pragma unroll
-  for (int img = 0; img < 2; ++img) {
+  {
     uint32_t *census = img ? p.census1 : p.census0;
     uint8_t *im = img ? p.im1 : p.im0;
     uint32_t rows_w[10][3]; // window rows 4*ty .. 4*ty+9, words tx, tx+1, tx+2
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) rows_w[r][c] = win[img][4 * ty + r][tx + c];
+      for (int c = 0; c < 3; ++c) rows_w[r][c] = win[0][4 * ty + r][tx + c];
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -325,11 +326,11 @@ __global__ void __launch_bounds__(F7_NT, 4) front7_kernel(const FrontParams p) {
 }
 
 cudaError_t launch_front(const FrontParams &p, cudaStream_t st) {
-  if (p.N > 65535) return cudaErrorInvalidValue;
+  if (p.N > 32767) return cudaErrorInvalidValue;
   if (p.cw == 7 && p.ch == 7) {
-    const dim3 grid((p.cols + F7_TW - 1) / F7_TW, (p.rows + F7_TH - 1) / F7_TH, p.N);
-    if (p.left_rgba) front7_kernel<true><<<grid, F7_NT, 0, st>>>(p);
-    else front7_kernel<false><<<grid, F7_NT, 0, st>>>(p);
+    const dim3 grid((p.cols + F7_TW - 1) / F7_TW, (p.rows + F7_TH - 1) / F7_TH, 2 * p.N);
+    if (p.left_rgba) front7_kernel<true, 4><<<grid, F7_NT, 0, st>>>(p);
+    else front7_kernel<false, 4><<<grid, F7_NT, 0, st>>>(p);
     return cudaGetLastError();
   }
   const dim3 grid((p.cols + FT - 1) / FT, (p.rows + FT - 1) / FT, p.N);
