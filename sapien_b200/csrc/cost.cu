@@ -293,6 +293,7 @@ static cudaError_t launch_cfg(const uint32_t *cL, const uint32_t *cR, uint16_t *
   const size_t smem = (size_t)BH * NS * TX * TD * sizeof(uint32_t) / (PACK8 ? 2 : 1);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
   if (g_sm_count == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -326,7 +327,9 @@ static cudaError_t launch_fast(const uint32_t *cL, const uint32_t *cR, uint16_t 
   if constexpr (BW == 7 && BH == 7) if (pack8) { // the stock block size: compile-time D for the usual disparity ranges
     if (D == 64) return launch_cfg<BW, BH, TX, 4, 32, true, 64>(cL, cR, C, N, rows, cols, D, st);
     if (D == 96) return launch_cfg<BW, BH, TX, 2, 64, true, 96>(cL, cR, C, N, rows, cols, D, st);
-    // TX = 32 at D >= 128: 38/32 instead of 22/16 Hamming columns per output column (measured 73.6 -> 69.5 us at C1)
+    // TX = 32 at D >= 128: 38/32 instead of 22/16 Hamming columns per output column (73.6 -> 69.5 us at C1).
+    // That variant uses 254 registers (2 blocks = 8 warps per SM); capping it at 168 or 128 registers
+    // for 12 / 16 warps measured 80 us and 113 us: the kernel wants instruction-level parallelism, not warps.
     if (D == 128) return launch_cfg<BW, BH, 32, 2, 64, true, 128>(cL, cR, C, N, rows, cols, D, st);
     if (D == 256) return launch_cfg<BW, BH, 32, 2, 64, true, 256>(cL, cR, C, N, rows, cols, D, st);
   }

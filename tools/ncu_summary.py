@@ -23,6 +23,9 @@ KEYS = [
     ("smsp__inst_executed.sum", "warp instructions"),
     ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU pipe % (int/DPX min-add live here)"),
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe %"),
+    ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU pipe % (POPC lives here)"),
+    ("sm__cycles_active.avg", "SM active cycles (avg)"),
+    ("sm__cycles_elapsed.avg", "SM elapsed cycles (avg)"),
     ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "ALU pipe cycles active %"),
     ("smsp__average_warp_latency_per_inst_issued.ratio", "warp cycles per issued instruction"),
     ("launch__registers_per_thread", "registers/thread"),
