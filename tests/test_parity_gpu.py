@@ -88,6 +88,22 @@ def test_other_cameras_vs_oracle(native, oracle, cfg):
     assert_depth_close(eng.get_ndarray(), ref["out"])
 
 
+@pytest.mark.parametrize("geom", [(331, 149, 128), (300, 157, 256), (203, 301, 64), (167, 33, 96)])
+def test_odd_geometry_vs_oracle(native, oracle, geom):
+    """Sizes that are multiples of nothing: ragged right-most cost blocks (EDGE variant at 16 and 32 columns per
+    thread), partial row bands, 2-3 rows per block in the final pass, partial last block."""
+    cols, rows, d = geom
+    base = configs._sensor_params("D415", max_disp=d, rectified=False, roll_deg=0.5,
+                                  scale=(cols, rows, (cols * 3) // 2, (rows * 3) // 2))
+    left, right = configs.pair(base, seed=cols)
+    ref = oracle.pipeline(base, left, right)
+    eng = run_ours(native, base, left, right, keep_stages=True)
+    assert_stages_equal(eng, base, ref)
+    assert_depth_close(eng.get_ndarray(), ref["out"])
+    fast = run_ours(native, base, left, right)
+    assert_stages_equal(fast, base, ref, names=("cost", "disp_wta", "disp_right", "disp_med", "depth"))
+
+
 @pytest.mark.parametrize("bbox", [(8, 4, 64, 40), (0, 0, 96, 64), (31, 23, 33, 37), (60, 30, 36, 34)])
 def test_small_bbox_vs_oracle(native, oracle, bbox):
     prm = configs.params("small")
