@@ -31,6 +31,7 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <cuda.h> // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cstdlib>
 
 namespace ssb {
@@ -47,7 +48,9 @@ struct AggrArgs {
   int vertical, reverse;
   uint32_t P1P1, P2P2;
   int uniq;
-  int nsm; // SM count: blocks b and b + nsm land on the same SM in the first wave
+  int nsm; // SM count
+  int tma;  // vertical passes: rows of a chunk arrive as ONE 2-D tensor copy per stream (tm[] valid)
+  alignas(64) CUtensorMap tm[3]; // C, aux0, aux1 viewed as [N*rows][cols*D] u16, box = [K][D]
 };
 
 // ---- optional per-block timeline (debug/profiling aid, tools/trace_aggr.py): when a buffer is
@@ -86,6 +89,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tma_g2s_2d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 
 template <int NR> __device__ __forceinline__ void lds_vec(const void *p, uint32_t (&r)[NR]) {
@@ -155,7 +163,7 @@ constexpr int WTA_TILES = 2; // LAll tiles (32 pixels each) between the SGM warp
 template <int MODE, int K, int NCH> __host__ __device__ inline AggrSmem aggr_smem(int D) {
   AggrSmem s;
   const int piece = D * 2;
-  s.ring = 64; // mbarriers first: NCH bulk-copy barriers, then (MODE 2) WTA_TILES full + WTA_TILES empty
+  s.ring = 128; // (tensor copies want a 128-byte aligned destination) mbarriers first: NCH bulk-copy barriers, then (MODE 2) WTA_TILES full + WTA_TILES empty
   s.tile = s.ring + nstream<MODE>() * NCH * K * piece;
   s.gk = s.tile + (MODE == 2 ? (WTA_TILES * 32 + 1) * (piece + 16) : 0); // +1 row: the consumer prefetches one row ahead
   s.rb = s.gk + (MODE == 2 ? 32 * 4 : 0);
@@ -171,6 +179,9 @@ template <int NS, int K, int NCH> struct PathRing {
   long sstride;
   int steps, PIECE, STREAM, lane;
   bool vertical, hrev;
+  // 2-D tensor-copy mode of vertical paths: box = K rows x one pixel's D costs
+  const CUtensorMap *tm;
+  int tma, c0, row0, vrev; // element column of the path, first row (n*rows [+ rows-1 when reversed]), direction
   __device__ __forceinline__ void init() const {
     if (lane == 0) {
 #pragma unroll
@@ -183,9 +194,22 @@ template <int NS, int K, int NCH> struct PathRing {
     const int s0 = ci * K;
     const int kc = min(K, steps - s0);
     const uint32_t bar = bar0 + 8 * slot;
+    const uint32_t dst = ring_s + (uint32_t)(slot * K * PIECE);
+    if (tma) {
+      // One instruction per stream instead of K row pieces (each UBLKCP of a divergent lane costs an
+      // ELECT / R2UR / branch round: ~10 instructions per piece, 3 pieces per step in the 3-stream
+      // pass).  The box is always K rows: rows past the path's end belong to the neighbouring
+      // environment or are out of bounds (zero filled) and are never consumed.
+      if (lane == 0) {
+        mbar_expect_tx(bar, (uint32_t)(K * PIECE * NS));
+        const int c1 = vrev ? row0 - s0 - (K - 1) : row0 + s0;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) tma_g2s_2d(dst + i * STREAM, tm + i, c0, c1, bar);
+      }
+      return;
+    }
     if (lane == 0) mbar_expect_tx(bar, (uint32_t)(kc * PIECE * NS));
     __syncwarp();
-    const uint32_t dst = ring_s + (uint32_t)(slot * K * PIECE);
     if (vertical) {
       if (lane < kc) {
         const long off = (long)(s0 + lane) * sstride;
@@ -222,7 +246,7 @@ __device__ __forceinline__ PathGeom path_geom(const AggrArgs &a, long path) {
 
 // ---- MODE 0 / 1: one independent warp per path ---------------------------------------------------
 template <int NR, int MODE, bool PARTIAL, bool DBG, int K, int NCH>
-__global__ void __launch_bounds__(128) aggr_kernel(const AggrArgs a) {
+__global__ void __launch_bounds__(128) aggr_kernel(const __grid_constant__ AggrArgs a) {
   static_assert(MODE == 0 || MODE == 1, "plain passes only");
   constexpr int DPL = 2 * NR;
   constexpr int NS = nstream<MODE>();
@@ -246,9 +270,11 @@ __global__ void __launch_bounds__(128) aggr_kernel(const AggrArgs a) {
   pr.g[2] = NS > 2 ? reinterpret_cast<const char *>(a.aux1 + pg.e0) : nullptr;
   pr.sstride = pg.sstride; pr.steps = steps; pr.PIECE = PIECE; pr.STREAM = NCH * K * PIECE; pr.lane = lane;
   pr.vertical = a.vertical != 0; pr.hrev = !a.vertical && a.reverse;
+  pr.tm = a.tm; pr.tma = a.tma && a.vertical; pr.vrev = a.reverse;
+  pr.c0 = pg.q * D; pr.row0 = pg.n * a.rows + (a.reverse ? a.rows - 1 : 0);
   const unsigned char *ring = wsm + lay.ring;
   const int STREAM = pr.STREAM;
-  const bool hrev = pr.hrev;
+  const bool hrev = pr.hrev || (pr.tma && a.reverse); // chunk rows lie in ascending address order: walk them backwards
 
   const int nact = D / DPL; // active lanes
   const bool active = !PARTIAL || lane < nact;
@@ -322,7 +348,7 @@ __global__ void __launch_bounds__(128) aggr_kernel(const AggrArgs a) {
       }
     } else {
       const int dp = hrev ? -PIECE : PIECE;
-      if (hrev) pc += (kc - 1) * PIECE;
+      if (hrev) pc += ((pr.tma ? K : kc) - 1) * PIECE; // a tensor box is always K rows, a bulk piece kc steps
       for (int k = 0; k < kc; ++k) { step(pc); pc += dp; }
     }
     if (++slot == NCH) { slot = 0; parity ^= 1; }
@@ -337,7 +363,7 @@ __global__ void __launch_bounds__(128) aggr_kernel(const AggrArgs a) {
 // Hand-over through two full/empty mbarrier pairs, so the serial SGM chain never waits for the
 // winner-takes-all arithmetic.
 template <int NR, bool PARTIAL, bool DBG, int K, int NCH>
-__global__ void __launch_bounds__(320) aggr_wta_kernel(const AggrArgs a) {
+__global__ void __launch_bounds__(320) aggr_wta_kernel(const __grid_constant__ AggrArgs a) {
   constexpr int DPL = 2 * NR;
   constexpr int NS = 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -395,7 +421,7 @@ __global__ void __launch_bounds__(320) aggr_wta_kernel(const AggrArgs a) {
     pr.g[1] = reinterpret_cast<const char *>(a.aux0 + pg.e0);
     pr.g[2] = nullptr;
     pr.sstride = pg.sstride; pr.steps = steps; pr.PIECE = PIECE; pr.STREAM = NCH * K * PIECE; pr.lane = lane;
-    pr.vertical = false; pr.hrev = false;
+    pr.vertical = false; pr.hrev = false; pr.tma = 0; pr.tm = nullptr; pr.c0 = pr.row0 = pr.vrev = 0;
     const unsigned char *ring = wsm + lay.ring;
     const int STREAM = pr.STREAM;
     const uint32_t selUp = lane == 0 ? 0x5454u : 0x5432u;
@@ -610,8 +636,35 @@ template <int NR> struct AggrCfg {
   template <int MODE> static constexpr int NCH() { return MODE == 0 ? 4 : 3; }
 };
 
+typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                           const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                           CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeTiledFn tensor_map_encoder() {
+  static TensorMapEncodeTiledFn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return reinterpret_cast<TensorMapEncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// volume [N][rows][cols][D] u16 as a 2-D tensor [N*rows][cols*D], box = K rows x D elements
+static bool make_volume_map(CUtensorMap *tm, const uint16_t *base, int N, int rows, int cols, int D, int K) {
+  TensorMapEncodeTiledFn enc = tensor_map_encoder();
+  if (!enc || !base) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols * D, (cuuint64_t)N * rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)cols * D * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)D, (cuuint32_t)K};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<uint16_t *>(base), gdim, gstride, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int NR, int MODE, bool PARTIAL, bool DBG, int NCHO = 0>
-static cudaError_t launch_one(const AggrArgs &a, cudaStream_t st) {
+static cudaError_t launch_one(const AggrArgs &a_in, cudaStream_t st) {
+  AggrArgs a = a_in;
+  a.tma = 0;
   constexpr int K = AggrCfg<NR>::template K<MODE>();
   constexpr int NCH = NCHO ? NCHO : AggrCfg<NR>::template NCH<MODE>();
   const size_t smem = (size_t)aggr_smem<MODE, K, NCH>(a.D).total; // per path
@@ -629,6 +682,13 @@ static cudaError_t launch_one(const AggrArgs &a, cudaStream_t st) {
     if (bsmem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem)) != cudaSuccess) return e;
     k<<<(unsigned)((npaths + ppb - 1) / ppb), (unsigned)(64 * ppb), bsmem, st>>>(a);
   } else {
+    static const bool no_tma = getenv("SSB_AGGR_NO_TMA") != nullptr;
+    if (a.vertical && !no_tma && a.D <= 256 && (long)a.cols * a.D * 2 % 16 == 0 && (long)a.N * a.rows < 0x7fffffffL) {
+      bool ok = make_volume_map(&a.tm[0], a.C, a.N, a.rows, a.cols, a.D, K);
+      if (MODE == 1) ok = ok && make_volume_map(&a.tm[1], a.aux0, a.N, a.rows, a.cols, a.D, K) &&
+                            make_volume_map(&a.tm[2], a.aux1, a.N, a.rows, a.cols, a.D, K);
+      a.tma = ok ? 1 : 0;
+    }
     auto k = aggr_kernel<NR, MODE, PARTIAL, DBG, K, NCH>;
     if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     k<<<(unsigned)npaths, 32, smem, st>>>(a);
@@ -692,9 +752,8 @@ cudaError_t launch_aggr_wta(const AggrBuffers &b, int N, int rows, int cols, int
   cudaError_t err;
   // right->left and top->bottom are independent.  Alone, each leaves HBM bandwidth unused (the
   // horizontal pass is bound by its 1280-step serial chain, 92 us + 92 us back to back); forked onto
-  // two streams with 2-slot rings -- so that the blocks of BOTH kernels are resident together --
-  // the pair takes 162 us.  SSB_AGGR_FORK=0 runs them back to back (4-slot rings), =1 forks with
-  // 3-slot rings (measured: no gain, the blocks do not all fit).
+  // two streams -- with the blocks of BOTH kernels resident together -- the pair takes 164 us.
+  // SSB_AGGR_FORK=0 runs them back to back.
   static const int fork = getenv("SSB_AGGR_FORK") ? atoi(getenv("SSB_AGGR_FORK")) : 2;
   AggrArgs h = a;
   h.vertical = 0; h.reverse = 1; h.out = b.L1;
@@ -703,8 +762,12 @@ cudaError_t launch_aggr_wta(const AggrBuffers &b, int N, int rows, int cols, int
   if (fork) {
     if ((err = cudaEventRecord(ev[0], stream)) != cudaSuccess) return err;
     if ((err = cudaStreamWaitEvent(s_aux, ev[0], 0)) != cudaSuccess) return err;
-    if ((err = (fork == 2 ? dispatch<0, 2>(v, s_aux) : dispatch<0, 3>(v, s_aux))) != cudaSuccess) return err;
-    if ((err = (fork == 2 ? dispatch<0, 2>(h, stream) : dispatch<0, 3>(h, stream))) != cudaSuccess) return err;
+    // ring depths measured on C1 (horizontal/vertical slots -> pair + following pass, us): 2/2 166+148, 3/2 166+140,
+    // 4/2 164+140, 2/3 172+148, 3/3 175+150, 4/3 177+146.  The latency-bound horizontal pass wants the deep
+    // ring; the vertical one (tensor copies) finishes last, which leaves its bottom rows in L2 for the
+    // bottom->top pass that starts there.
+    if ((err = dispatch<0, 2>(v, s_aux)) != cudaSuccess) return err;
+    if ((err = dispatch<0, 4>(h, stream)) != cudaSuccess) return err;
     if ((err = cudaEventRecord(ev[1], s_aux)) != cudaSuccess) return err;
     if ((err = cudaStreamWaitEvent(stream, ev[1], 0)) != cudaSuccess) return err;
     mark("aggr_left_down"); // one interval: the two kernels run concurrently

@@ -230,15 +230,19 @@ __global__ void __launch_bounds__(F7_NT, MINB) front7_kernel(const FrontParams p
   uint8_t *b0 = reinterpret_cast<uint8_t *>(&win[0][0][0]);
   constexpr int NEL = F7_WB * F7_WH;
   constexpr int NRND = (NEL + F7_NT - 1) / F7_NT; // texels per thread and image
-  constexpr int HALF = (NRND + 1) / 2;
+  constexpr int HALF = NRND; // one phase: every map load, then every texel load of the tile is in flight together
+  constexpr int NPH = (NRND + HALF - 1) / HALF;
   // Branch-free staging in three straight-line phases (map loads -> texel loads -> convert/store) so
   // that all loads of a phase are in flight together; out-of-image texels are loaded from a clamped
   // address and replaced by the zero padding of csct.cu:40-42 afterwards.
   {
     const Src &s = img ? sr : sl;
     uint8_t *bdst = b0;
+    const size_t envoff = (size_t)n * p.frows * p.fcols;
+    const float *srgba = RGBA ? s.rgba + 4 * envoff : nullptr;
+    const uint8_t *su8 = RGBA ? nullptr : s.u8 + envoff;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < NPH; ++h) {
       int fx[HALF], fy[HALF];
       bool inside[HALF];
       float mx[HALF], my[HALF];
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(F7_NT, MINB) front7_kernel(const FrontParams p
       }
       float tf[HALF];
       uint8_t tb[HALF];
-      size_t sp[HALF];
+      uint32_t sp[HALF]; // texel offset inside environment n (one image is < 4 Gi texels)
 #pragma unroll
       for (int k = 0; k < HALF; ++k) {
         if (s.mapx) { // camera.cu:83-119: always-snapped nearest neighbour
@@ -266,16 +270,16 @@ __global__ void __launch_bounds__(F7_NT, MINB) front7_kernel(const FrontParams p
           const float sy = fminf(fmaxf(roundf(my[k]), 0.0f), (float)(p.frows - 1));
           fx[k] = (int)sx; fy[k] = (int)sy;
         }
-        sp[k] = ((size_t)n * p.frows + fy[k]) * p.fcols + fx[k];
-        if (RGBA) tf[k] = __ldg(s.rgba + 4 * sp[k]);
-        else tb[k] = __ldg(s.u8 + sp[k]);
+        sp[k] = (uint32_t)fy[k] * (uint32_t)p.fcols + (uint32_t)fx[k];
+        if (RGBA) tf[k] = __ldg(srgba + 4 * (size_t)sp[k]);
+        else tb[k] = __ldg(su8 + sp[k]);
       }
 #pragma unroll
       for (int k = 0; k < HALF; ++k) {
         int v;
         if (RGBA) v = min(max((int)(tf[k] * 255), 0), 255); // truncation, core.cu:51
         else v = tb[k];
-        if (p.speckle_shape > 0.0f) v = ir_noise(p, v, sp[k], img);
+        if (p.speckle_shape > 0.0f) v = ir_noise(p, v, envoff + sp[k], img);
         const int e = (h * HALF + k) * F7_NT + tid;
         if (e < NEL) bdst[e] = (uint8_t)(inside[k] ? v : 0);
       }
