@@ -106,6 +106,14 @@ int ss_get_device(const ss_engine *e, int32_t *device);
 
 /* E:63 getMat2d / P:101: depth float32 [batch][out_rows][out_cols] copied to `out`. */
 int ss_get_depth_host(ss_engine *e, float *out, size_t capacity_bytes);
+/* Extension (no reference counterpart; the reference stages every read-back through an engine-owned
+ * pageable buffer, C:347-362): bind a HOST buffer [batch][out_rows][out_cols] float32 -- pinned for
+ * the copies to be asynchronous -- that every following compute streams its depth map into, band by
+ * band, while the final aggregation pass is still running (the pass runs in column segments; the
+ * finished columns are post-processed and copied behind each segment).  ss_get_depth_host() with
+ * this same pointer then only waits for the frame.  NULL unbinds.  The buffer must stay valid until
+ * it is unbound or the engine is destroyed.  Results are bit-identical to the unbound path. */
+int ss_bind_output_host(ss_engine *e, float *out, size_t capacity_bytes);
 /* E:67 getCudaPtr / P:103-111: borrowed device pointer. */
 int ss_get_depth_device(ss_engine *e, void **ptr);
 /* E:65 getPointCloudMat2d / P:122: float32 [batch][out_rows*out_cols][3]. */

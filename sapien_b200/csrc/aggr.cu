@@ -49,6 +49,11 @@ struct AggrArgs {
   uint32_t P1P1, P2P2;
   int uniq;
   int nsm; // SM count
+  // final pass only: after the columns < seg_end[k] of a row are finished (disparities written),
+  // its consumer warp bumps progress[k]; a stream can wait on the counter (cuStreamWaitValue32) and
+  // post-process / copy those columns while the pass is still running
+  uint32_t *progress;
+  int nseg, seg_end[6];
   int tma;  // vertical passes: rows of a chunk arrive as ONE 2-D tensor copy per stream (tm[] valid)
   alignas(64) CUtensorMap tm[3]; // C, aux0, aux1 viewed as [N*rows][cols*D] u16, box = [K][D]
 };
@@ -587,6 +592,7 @@ __global__ void __launch_bounds__(320) aggr_wta_kernel(const __grid_constant__ A
     __syncwarp();
   };
 
+  int nextseg = 0;
   for (int t = 0; t < ntiles; ++t) {
     const int ts = t % WTA_TILES;
     mbar_wait(barFull + 8 * ts, (uint32_t)((t / WTA_TILES) & 1));
@@ -616,6 +622,12 @@ __global__ void __launch_bounds__(320) aggr_wta_kernel(const __grid_constant__ A
     if (lane == 0) {
       const uint32_t bar = barEmpty + 8 * ts;
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+    }
+    if (nextseg < a.nseg && t0 + cnt >= a.seg_end[nextseg]) { // publish: this row is done up to the segment end
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) atomicAdd(a.progress + nextseg, 1u);
+      ++nextseg;
     }
   }
   if (active) {
@@ -683,7 +695,9 @@ static cudaError_t launch_one(const AggrArgs &a_in, cudaStream_t st) {
     k<<<(unsigned)((npaths + ppb - 1) / ppb), (unsigned)(64 * ppb), bsmem, st>>>(a);
   } else {
     static const bool no_tma = getenv("SSB_AGGR_NO_TMA") != nullptr;
-    if (a.vertical && !no_tma && a.D <= 256 && (long)a.cols * a.D * 2 % 16 == 0 && (long)a.N * a.rows < 0x7fffffffL) {
+    // (rows of D*2 bytes that are not whole 128-byte lines -- D = 96 -- measured slower as tensor boxes
+    // than as bulk pieces: C3 top->bottom 1.61 ms vs 1.74 ms)
+    if (a.vertical && !no_tma && a.D <= 256 && a.D * 2 % 128 == 0 && (long)a.N * a.rows < 0x7fffffffL) {
       bool ok = make_volume_map(&a.tm[0], a.C, a.N, a.rows, a.cols, a.D, K);
       if (MODE == 1) ok = ok && make_volume_map(&a.tm[1], a.aux0, a.N, a.rows, a.cols, a.D, K) &&
                             make_volume_map(&a.tm[2], a.aux1, a.N, a.rows, a.cols, a.D, K);
@@ -729,27 +743,30 @@ bool aggr_fast_supported(int D, int cmax, int P1, int P2) {
   return 4L * ((long)cmax + P2) <= 65535L && (long)cmax + P2 + P1 <= 65535L;
 }
 
-cudaError_t launch_aggr_wta(const AggrBuffers &b, int N, int rows, int cols, int D, int P1, int P2,
-                            int uniq, cudaStream_t stream, cudaStream_t s_aux, cudaEvent_t *ev,
-                            const AggrMarks *marks) {
-  auto mark = [&](const char *name) { if (marks) marks->mark(marks->ctx, name); };
+static cudaError_t common_args(AggrArgs &a, const AggrBuffers &b, int N, int rows, int cols, int D, int P1, int P2, int uniq) {
   if ((long)N * (rows > cols ? rows : cols) > 0x7fffffffL) return cudaErrorInvalidValue;
-  AggrArgs a{};
   a.C = b.C;
   a.N = N; a.rows = rows; a.cols = cols; a.D = D;
   a.P1P1 = (uint32_t)P1 * 0x10001u;
   a.P2P2 = (uint32_t)P2 * 0x10001u;
   a.uniq = uniq;
-  {
-    static int nsm = 0;
-    if (nsm == 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) nsm = 148;
-    }
-    a.nsm = nsm;
+  static int nsm = 0;
+  if (nsm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) nsm = 148;
   }
+  a.nsm = nsm;
+  return cudaSuccess;
+}
+
+cudaError_t launch_aggr_passes(const AggrBuffers &b, int N, int rows, int cols, int D, int P1, int P2,
+                               int uniq, cudaStream_t stream, cudaStream_t s_aux, cudaEvent_t *ev,
+                               const AggrMarks *marks) {
+  auto mark = [&](const char *name) { if (marks) marks->mark(marks->ctx, name); };
+  AggrArgs a{};
   cudaError_t err;
+  if ((err = common_args(a, b, N, rows, cols, D, P1, P2, uniq)) != cudaSuccess) return err;
   // right->left and top->bottom are independent.  Alone, each leaves HBM bandwidth unused (the
   // horizontal pass is bound by its 1280-step serial chain, 92 us + 92 us back to back); forked onto
   // two streams -- with the blocks of BOTH kernels resident together -- the pair takes 164 us.
@@ -782,12 +799,33 @@ cudaError_t launch_aggr_wta(const AggrBuffers &b, int N, int rows, int cols, int
   u.vertical = 1; u.reverse = 1; u.aux0 = b.L1; u.aux1 = b.L2; u.out = b.S3; u.dbg0 = b.dbgL3;
   if ((err = dispatch<1>(u, stream)) != cudaSuccess) return err;
   mark("aggr_up");
-  // left->right + blend + winner-takes-all
-  AggrArgs w = a;
+  return cudaSuccess;
+}
+
+// left->right + blend + winner-takes-all; optional progress counters (see AggrArgs)
+cudaError_t launch_aggr_final(const AggrBuffers &b, int N, int rows, int cols, int D, int P1, int P2,
+                              int uniq, cudaStream_t stream, uint32_t *progress, int nseg, const int *seg_end) {
+  if (nseg < 0 || nseg > 6 || (nseg && (!progress || !seg_end))) return cudaErrorInvalidValue;
+  AggrArgs w{};
+  cudaError_t err;
+  if ((err = common_args(w, b, N, rows, cols, D, P1, P2, uniq)) != cudaSuccess) return err;
   w.vertical = 0; w.reverse = 0; w.aux0 = b.S3; w.dbg0 = b.dbgL0; w.dbg1 = b.dbgLAll;
   w.dispL = b.dispL; w.dispR = b.dispR;
-  err = dispatch<2>(w, stream);
-  mark("aggr_right_wta");
+  w.progress = progress; w.nseg = nseg;
+  for (int i = 0; i < nseg; ++i) {
+    if ((seg_end[i] & 31) || seg_end[i] <= (i ? seg_end[i - 1] : 0) || seg_end[i] >= cols) return cudaErrorInvalidValue;
+    w.seg_end[i] = seg_end[i];
+  }
+  return dispatch<2>(w, stream);
+}
+
+cudaError_t launch_aggr_wta(const AggrBuffers &b, int N, int rows, int cols, int D, int P1, int P2,
+                            int uniq, cudaStream_t stream, cudaStream_t s_aux, cudaEvent_t *ev,
+                            const AggrMarks *marks) {
+  cudaError_t err = launch_aggr_passes(b, N, rows, cols, D, P1, P2, uniq, stream, s_aux, ev, marks);
+  if (err != cudaSuccess) return err;
+  err = launch_aggr_final(b, N, rows, cols, D, P1, P2, uniq, stream, nullptr, 0, nullptr);
+  if (marks) marks->mark(marks->ctx, "aggr_right_wta");
   return err;
 }
 

@@ -9,7 +9,10 @@
 #include "kernels.h"
 
 #include <algorithm>
+#include <climits>
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -69,9 +72,19 @@ int validate_params(const ss_config &c) {
 struct ss_engine {
   ss_config cfg{};
   int device = 0;
-  cudaStream_t stream = nullptr, aux = nullptr;
+  cudaStream_t stream = nullptr, aux = nullptr, cpy = nullptr;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  // banded output (ss_bind_output_host): the final SGM pass runs in column segments and the depth map
+  // streams to the bound host buffer band by band while the remaining segments compute
+  static constexpr int MAXSEG = 6;
+  cudaEvent_t ev_seg[MAXSEG] = {}, ev_band[MAXSEG] = {}, ev_copied = nullptr;
+  float *host_out = nullptr;
+  size_t host_cap = 0;
+  bool streamed = false;        // the last compute delivered its depth map into host_out
+  std::vector<int> rgb_sufmin;  // [cols+1] smallest RGB column any matched column >= x can splat into (empty: banding off)
+  uint32_t *progress = nullptr; // [MAXSEG] rows finished per column segment of the final pass
+
   std::vector<void *> allocs;
   float *mapLx = nullptr, *mapLy = nullptr, *mapRx = nullptr, *mapRy = nullptr;
   float *a1 = nullptr, *a2 = nullptr, *a3 = nullptr;
@@ -136,7 +149,11 @@ int create_impl(ss_engine *e, const float *mapLx, const float *mapLy, const floa
   const ss_config &c = e->cfg;
   CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&e->cpy, cudaStreamNonBlocking));
   for (auto &ev : e->ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto &ev : e->ev_seg) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto &ev : e->ev_band) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&e->ev_copied, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
   const size_t fsz = e->fsz(), N = (size_t)c.batch;
@@ -153,6 +170,27 @@ int create_impl(ss_engine *e, const float *mapLx, const float *mapLy, const floa
     if ((r = upload(e, &e->a1, a1, fsz))) return r;
     if ((r = upload(e, &e->a2, a2, fsz))) return r;
     if ((r = upload(e, &e->a3, a3, fsz))) return r;
+  }
+  // Banded output needs, per matched column, the left-most RGB column it can reach (depth_and_splat in
+  // post.cu: x = (a1 z + b1) / (a3 z + b3), z in [f b / D, inf) -- monotone in z while a3 z + b3 > 0).
+  e->rgb_sufmin.clear();
+  if (c.registration) {
+    const double zmin = (double)c.focal_len * c.baseline_len / (double)c.max_disp;
+    bool ok = zmin > 0;
+    std::vector<int> colmin(c.cols, INT32_MAX);
+    for (uint32_t y = 0; ok && y < c.rows; ++y)
+      for (uint32_t x = 0; x < c.cols; ++x) {
+        const size_t i = (size_t)y * c.cols + x;
+        const double den0 = (double)a3[i] * zmin + c.b3;
+        if (!(a3[i] > 0) || !(den0 > 0)) { ok = false; break; }
+        const double x0 = ((double)a1[i] * zmin + c.b1) / den0, x1 = (double)a1[i] / (double)a3[i];
+        const double lo = std::floor(std::min(x0, x1)) - 1.0;
+        colmin[x] = std::min<double>(colmin[x], std::max(lo, -1.0e9));
+      }
+    if (ok) {
+      e->rgb_sufmin.assign(c.cols + 1, INT32_MAX);
+      for (int x = (int)c.cols - 1; x >= 0; --x) e->rgb_sufmin[x] = std::min(e->rgb_sufmin[x + 1], colmin[x]);
+    }
   }
   // cost volumes: C, L1, L2 (S3 aliases L2) -- or 7 separate ones with keep_stages
   const size_t vol = fsz * (size_t)c.max_disp * sizeof(uint16_t);
@@ -228,6 +266,21 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
   if (!fast) { int r = e->ensure_generic_volumes(); if (r) return r; }
   const size_t fsz = e->fsz(), msz = (size_t)rows * cols;
   int launches = 0;
+  // Banded output plan (see ss_bind_output_host): up to 5 progress points of the final pass -> up to 6 bands
+  int nseg = 0, seg_end[ss_engine::MAXSEG];
+  bool banded = false;
+  if (e->host_out && fast && !use_bbox && !c.keep_stages && c.batch <= e->wave &&
+      (!c.registration || !e->rgb_sufmin.empty())) {
+    static const float frac[5] = {0.2f, 0.4f, 0.6f, 0.8f, 0.95f};
+    for (float f : frac) {
+      const int x = ((int)(cols * f) / 32) * 32;
+      if (x - D - c.mf_size / 2 >= 32 && x > (nseg ? seg_end[nseg - 1] : 0) && x < cols) seg_end[nseg++] = x;
+    }
+    if (nseg > 0) {
+      banded = true; // (the last band, up to cols, follows the end of the kernel)
+      if (!e->progress) { int r = e->alloc(&e->progress, ss_engine::MAXSEG); if (r) return r; }
+    }
+  }
   for (int w0 = 0; w0 < c.batch; w0 += e->wave) {
     const int wn = std::min(e->wave, c.batch - w0);
     FrontParams fp{};
@@ -261,8 +314,14 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
     if (fast) {
       if (!c.keep_stages) { ab.dbgL0 = ab.dbgL3 = ab.dbgLAll = nullptr; }
       AggrMarks am{[](void *ctx, const char *name) { static_cast<ss_engine *>(ctx)->mark(name); }, e};
-      CK(launch_aggr_wta(ab, wn, rows, cols, D, P1, P2, c.uniq_ratio, st, e->aux, e->ev, e->profiling ? &am : nullptr));
-      launches += 6;
+      if (banded) { // the final pass follows below, with its progress counters
+        CK(launch_aggr_passes(ab, wn, rows, cols, D, P1, P2, c.uniq_ratio, st, e->aux, e->ev, e->profiling ? &am : nullptr));
+        launches += 3;
+      } else {
+        CK(launch_aggr_wta(ab, wn, rows, cols, D, P1, P2, c.uniq_ratio, st, e->aux, e->ev, e->profiling ? &am : nullptr));
+        launches += 4;
+      }
+      launches += 2;
     } else {
       CK(launch_aggr_wta_generic(ab, nullptr, wn, rows, cols, D, P1, P2, c.uniq_ratio, st));
       launches += 8;
@@ -283,9 +342,61 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
   pp.rgb_rows = (int)c.rgb_rows; pp.rgb_cols = (int)c.rgb_cols;
   pp.canvas = e->canvas; pp.out = e->out;
   pp.canvas_prefilled = 1;
-  int pl = 0;
-  CK(launch_post(pp, st, &pl));
-  launches += pl;
+  e->streamed = false;
+  if (banded) {
+    // final pass in column segments; behind each segment: post-processing of the columns whose
+    // disparities are final (helper stream) and the copy of the finished output columns to the bound
+    // host buffer (copy stream), both overlapping the next segment
+    AggrBuffers ab{};
+    ab.C = e->C; ab.L1 = e->L1; ab.L2 = e->L2; ab.S3 = e->S3;
+    ab.dispL = e->dispL; ab.dispR = e->dispR;
+    const int H = c.mf_size / 2, ocols = (int)e->out_cols(), orows = (int)e->out_rows();
+    const size_t pitch = (size_t)ocols * sizeof(float);
+    CK(cudaMemsetAsync(e->progress, 0, ss_engine::MAXSEG * sizeof(uint32_t), st));
+    CK(cudaEventRecord(e->ev_seg[0], st));
+    CK(cudaStreamWaitEvent(e->aux, e->ev_seg[0], 0)); // counters are zero before anybody waits on them
+    CK(launch_aggr_final(ab, c.batch, rows, cols, D, P1, P2, c.uniq_ratio, st, e->progress, nseg, seg_end));
+    ++launches;
+    CK(cudaEventRecord(e->ev_seg[1], st)); // end of the pass: the last band
+    int xa = 0, ua = 0;
+    for (int s = 0; s <= nseg; ++s) {
+      const bool last = s == nseg;
+      if (last) { // the columns behind the last progress point: after the pass itself
+        CK(cudaStreamWaitEvent(e->aux, e->ev_seg[1], 0));
+        pp.wait_ctr = nullptr; pp.wait_target = 0;
+      } else { // the band's blocks start now and wait until every row has passed seg_end[s]
+        pp.wait_ctr = e->progress + s; pp.wait_target = (uint32_t)c.batch * (uint32_t)rows;
+      }
+      // LR check reads dispR up to D-1 columns back (final D-1 columns behind the pass), the median H columns ahead
+      const int xb = last ? cols : std::max(xa, ((seg_end[s] - D - H) / 32) * 32);
+      int ub;
+      if (last) ub = ocols;
+      else if (c.registration) ub = std::min(ocols, std::max(ua, ((e->rgb_sufmin[xb] - 2) / 4) * 4)); // dilation reads one column ahead
+      else ub = xb;
+      pp.xa = xa; pp.xb = xb; pp.ua = c.registration ? ua : 0; pp.ub = c.registration ? ub : 0;
+      if (xb > xa || (c.registration && ub > ua)) {
+        int pl = 0;
+        CK(launch_post(pp, e->aux, &pl));
+        launches += pl;
+      }
+      CK(cudaEventRecord(e->ev_band[s], e->aux));
+      if (ub > ua) {
+        CK(cudaStreamWaitEvent(e->cpy, e->ev_band[s], 0));
+        CK(cudaMemcpy2DAsync(e->host_out + ua, pitch, e->out + ua, pitch, (size_t)(ub - ua) * sizeof(float),
+                             (size_t)c.batch * orows, cudaMemcpyDeviceToHost, e->cpy));
+      }
+      xa = xb; ua = ub;
+    }
+    e->mark("aggr_right_wta");
+    CK(cudaEventRecord(e->ev_copied, e->cpy));
+    CK(cudaStreamWaitEvent(st, e->ev_band[nseg], 0));
+    CK(cudaStreamWaitEvent(st, e->ev_copied, 0));
+    e->streamed = true;
+  } else {
+    int pl = 0;
+    CK(launch_post(pp, st, &pl));
+    launches += pl;
+  }
   e->mark("post");
   e->launches = launches;
   e->mrows = rows; e->mcols = cols;
@@ -344,6 +455,10 @@ int ss_destroy(ss_engine *e) {
   for (void *p : e->allocs) cudaFree(p);
   for (auto ev : e->pev) cudaEventDestroy(ev);
   for (auto ev : e->ev) if (ev) cudaEventDestroy(ev);
+  for (auto ev : e->ev_seg) if (ev) cudaEventDestroy(ev);
+  for (auto ev : e->ev_band) if (ev) cudaEventDestroy(ev);
+  if (e->ev_copied) cudaEventDestroy(e->ev_copied);
+  if (e->cpy) { cudaStreamSynchronize(e->cpy); cudaStreamDestroy(e->cpy); }
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_out) cudaEventDestroy(e->ev_out);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -411,7 +526,22 @@ int ss_get_depth_host(ss_engine *e, float *out, size_t cap) {
   if (!e) return fail(SS_ERR_INVALID, "null engine");
   if (!e->computed) return fail(SS_ERR_NOT_COMPUTED, "No computed data stored");
   DeviceGuard g(e->device);
+  if (e->streamed && out == e->host_out) { // already delivered band by band during compute
+    CK(cudaStreamSynchronize(e->stream));
+    return SS_OK;
+  }
   return copy_out(e, e->out, (size_t)e->cfg.batch * e->rsz(), out, cap);
+}
+
+int ss_bind_output_host(ss_engine *e, float *out, size_t cap) {
+  if (!e) return fail(SS_ERR_INVALID, "null engine");
+  if (out && cap < (size_t)e->cfg.batch * e->rsz() * sizeof(float)) return fail(SS_ERR_INVALID, "output buffer too small");
+  DeviceGuard g(e->device);
+  CK(cudaStreamSynchronize(e->stream)); // a frame may still be streaming into the previous binding
+  e->host_out = out;
+  e->host_cap = out ? cap : 0;
+  e->streamed = false;
+  return SS_OK;
 }
 int ss_get_depth_device(ss_engine *e, void **ptr) {
   if (!e || !ptr) return fail(SS_ERR_INVALID, "null argument");

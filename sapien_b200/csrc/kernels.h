@@ -59,6 +59,16 @@ struct AggrMarks { // optional per-kernel timing marks (engine profiling mode)
 cudaError_t launch_aggr_wta(const AggrBuffers &b, int N, int rows, int cols, int D, int P1, int P2,
                             int uniq, cudaStream_t stream, cudaStream_t s_aux, cudaEvent_t *ev,
                             const AggrMarks *marks = nullptr);
+// The same in two parts: the three plain passes, then the final pass (left->right + blend +
+// winner-takes-all).  With progress counters the final pass reports, per row, when the columns
+// < seg_end[k] (multiples of 32, ascending, < cols) are finished: progress[k] reaches N*rows when
+// every row is that far -- disparities of the columns < seg_end[k] - D are then final (the right
+// disparity of a pixel completes D-1 columns later).  The caller zeroes the counters beforehand.
+cudaError_t launch_aggr_passes(const AggrBuffers &b, int N, int rows, int cols, int D, int P1, int P2,
+                               int uniq, cudaStream_t stream, cudaStream_t s_aux, cudaEvent_t *ev,
+                               const AggrMarks *marks = nullptr);
+cudaError_t launch_aggr_final(const AggrBuffers &b, int N, int rows, int cols, int D, int P1, int P2,
+                              int uniq, cudaStream_t stream, uint32_t *progress, int nseg, const int *seg_end);
 // Generic (any D, 32-bit math) fallback with the same contract; needs scratch volumes.
 cudaError_t launch_aggr_wta_generic(const AggrBuffers &b, uint16_t *L0scratch, int N, int rows,
                                     int cols, int D, int P1, int P2, int uniq,
@@ -87,6 +97,15 @@ struct PostParams {
   float *canvas;   // [N][rgb_rows][rgb_cols] splat target
   int canvas_prefilled; // 1: the front-end kernel already filled the canvas with max_depth
   float *out;      // final depth: [N][rgb_rows][rgb_cols] or [N][frows][fcols]
+  // Column band (all zero = the whole frame).  LR check + median + depth + splat run on the matched
+  // columns [xa, xb) (xa % 32 == 0), dilation + range clamp on the RGB columns [ua, ub)
+  // (ua % 4 == 0); the bands of one frame are launched left to right on one stream and replace the
+  // whole-frame call (the canvas is prefilled by the front-end).  No ROI mode.
+  int xa, xb, ua, ub;
+  // optional: the band's kernels start early and their blocks wait (one polling thread each, with
+  // back-off) until *wait_ctr >= wait_target -- the progress counter of the final aggregation pass
+  const uint32_t *wait_ctr;
+  uint32_t wait_target;
 };
 cudaError_t launch_post(const PostParams &p, cudaStream_t stream, int *launches);
 

@@ -72,6 +72,20 @@ __device__ __forceinline__ void depth_and_splat(const PostParams &p, size_t n, s
   }
 }
 
+// Blocks of a band launched ahead of its data: wait for the producer's progress counter.
+__device__ __forceinline__ void wait_progress(const PostParams &p, bool leader) {
+  if (!p.wait_ctr) return;
+  if (leader) {
+    unsigned v;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.wait_ctr) : "memory");
+      if (v >= p.wait_target) break;
+      __nanosleep(1000);
+    }
+  }
+  __syncthreads();
+}
+
 // FUSE: no ROI -> the matched image is the full image, so depth + splat run in the same thread.
 template <int K, bool FUSE>
 __global__ void __launch_bounds__(PT_X *PT_Y) lr_median_kernel(const PostParams p) {
@@ -79,9 +93,10 @@ __global__ void __launch_bounds__(PT_X *PT_Y) lr_median_kernel(const PostParams 
   constexpr int WC = PT_X + 2 * H, WR = PT_Y + 2 * H;
   __shared__ float tile[WR][WC];
   const int n = blockIdx.z;
-  const int x0 = blockIdx.x * PT_X, y0 = blockIdx.y * PT_Y;
+  const int x0 = p.xa + blockIdx.x * PT_X, y0 = blockIdx.y * PT_Y; // columns [xa, xb) of every row
   const size_t img = (size_t)n * p.rows * p.cols;
   const int tid = threadIdx.y * PT_X + threadIdx.x;
+  wait_progress(p, tid == 0);
   // Tile load in straight-line phases (left disparities, then the dependent right-disparity
   // gathers) so that the loads of all rounds are in flight together.
   constexpr int NT = PT_X * PT_Y, NEL = WR * WC, NRND = (NEL + NT - 1) / NT;
@@ -122,7 +137,7 @@ __global__ void __launch_bounds__(PT_X *PT_Y) lr_median_kernel(const PostParams 
   }
   __syncthreads();
   const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-  if (x >= p.cols || y >= p.rows) return;
+  if (x >= p.xb || y >= p.rows) return;
   float out = tile[threadIdx.y + H][threadIdx.x + H];
   if (K > 1 && x >= H && y >= H && x < p.cols - H && y < p.rows - H) { // filter.cu:107
     constexpr int NN = K * K;
@@ -166,9 +181,10 @@ __global__ void __launch_bounds__(256) depth_splat_kernel(const PostParams p) { 
 // out(x,y) = min over the 2x2 block (x..x+1, y..y+1) of the inputs that are < maxDepth.
 // 2-D grid (no index divisions), 4 pixels per thread.
 __global__ void __launch_bounds__(128) dilate_range_kernel(const PostParams p) {
-  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  wait_progress(p, threadIdx.x == 0);
+  const int x4 = p.ua + (blockIdx.x * blockDim.x + threadIdx.x) * 4; // columns [ua, ub): ua % 4 == 0
   const int y = blockIdx.y;
-  if (x4 >= p.rgb_cols) return;
+  if (x4 >= p.ub) return;
   const size_t row = ((size_t)blockIdx.z * p.rgb_rows + y) * p.rgb_cols;
   const float *r0 = p.canvas + row + x4;
   const bool yb = y + 1 < p.rgb_rows;
@@ -211,8 +227,12 @@ __global__ void __launch_bounds__(128) dilate_range_kernel(const PostParams p) {
   }
 }
 
-cudaError_t launch_post(const PostParams &p, cudaStream_t st, int *launches) {
+cudaError_t launch_post(const PostParams &p_in, cudaStream_t st, int *launches) {
+  PostParams p = p_in;
   if (p.N > 65535) return cudaErrorInvalidValue;
+  const bool band = p.xb > 0 || p.ub > 0; // a column band of a frame whose setup launches already ran
+  if (!band) { p.xa = 0; p.xb = p.cols; p.ua = 0; p.ub = p.rgb_cols; }
+  if (band && (p.bbox || (p.xa & 31) || (p.ua & 3) || p.xb > p.cols || p.ub > p.rgb_cols)) return cudaErrorInvalidValue;
   int nl = 0;
   cudaError_t err;
   const size_t fsz = (size_t)p.frows * p.fcols * p.N;
@@ -220,29 +240,31 @@ cudaError_t launch_post(const PostParams &p, cudaStream_t st, int *launches) {
   if (p.bbox) { // outside-ROI disparity is defined as 0 (reference leaves it uninitialised)
     if ((err = cudaMemsetAsync(p.disp_full, 0, fsz * sizeof(float), st)) != cudaSuccess) return err;
   }
-  if (p.registration && !p.canvas_prefilled) {
+  if (p.registration && !p.canvas_prefilled && !band) {
     fill_kernel<<<(unsigned)min((rsz + 255) / 256, (size_t)148 * 16), 256, 0, st>>>(p.canvas, rsz, p.max_depth);
     ++nl;
   }
-  const dim3 grid((p.cols + PT_X - 1) / PT_X, (p.rows + PT_Y - 1) / PT_Y, p.N);
+  const dim3 grid((p.xb - p.xa + PT_X - 1) / PT_X, (p.rows + PT_Y - 1) / PT_Y, p.N);
   const dim3 block(PT_X, PT_Y);
 #define SSB_MED(KK)                                                                               \
   case KK:                                                                                        \
     if (p.bbox) lr_median_kernel<KK, false><<<grid, block, 0, st>>>(p);                           \
     else lr_median_kernel<KK, true><<<grid, block, 0, st>>>(p);                                   \
     break;
-  switch (p.mf_size) {
-    SSB_MED(1) SSB_MED(3) SSB_MED(5) SSB_MED(7)
-  default: return cudaErrorInvalidValue;
+  if (p.xb > p.xa) {
+    switch (p.mf_size) {
+      SSB_MED(1) SSB_MED(3) SSB_MED(5) SSB_MED(7)
+    default: return cudaErrorInvalidValue;
+    }
+    ++nl;
   }
 #undef SSB_MED
-  ++nl;
   if (p.bbox) {
     depth_splat_kernel<<<(unsigned)((fsz + 255) / 256), 256, 0, st>>>(p);
     ++nl;
   }
-  if (p.registration) {
-    const dim3 dg((unsigned)((p.rgb_cols + 4 * 128 - 1) / (4 * 128)), (unsigned)p.rgb_rows, (unsigned)p.N);
+  if (p.registration && p.ub > p.ua) {
+    const dim3 dg((unsigned)((p.ub - p.ua + 4 * 128 - 1) / (4 * 128)), (unsigned)p.rgb_rows, (unsigned)p.N);
     dilate_range_kernel<<<dg, 128, 0, st>>>(p);
     ++nl;
   }

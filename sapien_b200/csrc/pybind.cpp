@@ -232,6 +232,16 @@ public:
     check(ss_get_depth_host(e_, out.mutable_data(), (size_t)out.nbytes()));
     return out;
   }
+  // extension: every following compute() streams its depth map into `out` (pinned float32 ndarray of
+  // the get_ndarray shape) while the last aggregation pass is still running; get_ndarray(out=out)
+  // then only waits.  None unbinds.  The engine keeps a reference to the array.
+  void bindOutput(py::object out_arg) {
+    if (out_arg.is_none()) { check(ss_bind_output_host(e_, nullptr, 0)); bound_ = py::none(); return; }
+    auto out = out_arg.cast<py::array_t<float, py::array::c_style>>();
+    if (out.ptr() != out_arg.ptr()) throw py::type_error("out must be a C-contiguous float32 ndarray");
+    check(ss_bind_output_host(e_, out.mutable_data(), (size_t)out.nbytes()));
+    bound_ = out_arg;
+  }
   CudaArray getCuda() {
     void *p = nullptr;
     check(ss_get_depth_device(e_, &p));
@@ -338,6 +348,7 @@ private:
   uint32_t rows_ = 0, cols_ = 0, orows_ = 0, ocols_ = 0;
   int32_t device_ = 0;
   int batch_ = 1;
+  py::object bound_ = py::none();
 };
 
 } // namespace
@@ -400,6 +411,7 @@ PYBIND11_MODULE(_simsense_b200, m) {
            "bbox_start_x"_a = 0, "bbox_start_y"_a = 0, "bbox_width"_a = 0, "bbox_height"_a = 0,
            "stream"_a = py::none(), "sync"_a = true)
       .def("get_ndarray", &E::getNdarray, "out"_a = py::none())
+      .def("bind_output", &E::bindOutput, "out"_a)
       .def("get_cuda", &E::getCuda)
       .def("get_point_cloud_cuda", &E::getPointCloudCuda)
       .def("get_point_cloud_ndarray", &E::getPointCloudNdarray)

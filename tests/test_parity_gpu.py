@@ -104,6 +104,42 @@ def test_odd_geometry_vs_oracle(native, oracle, geom):
     assert_stages_equal(fast, base, ref, names=("cost", "disp_wta", "disp_right", "disp_med", "depth"))
 
 
+@pytest.mark.parametrize("cfg,over", [("C1", {}), ("C1", dict(mf_size=7, lr_max_diff=3)), ("C1r", dict(dilation=False)),
+                                      ("C3", {}), ("C5", {}), ("odd", {}), ("small", {})])
+def test_banded_output_is_bit_identical(native, cfg, over):
+    """bind_output(): the final pass runs in column segments and the depth map streams to the bound host buffer
+    band by band.  Every stage and the delivered map must equal the unbanded run bit for bit (frames back to back,
+    so that stale state of one frame would show in the next)."""
+    import torch
+
+    if cfg == "odd":
+        prm = configs._sensor_params("D415", max_disp=64, rectified=False, roll_deg=0.5, scale=(523, 211, 700, 300))
+    else:
+        prm = variant(configs.params(cfg), **over)
+    plain = make_engine(native, prm)
+    band = make_engine(native, prm)
+    out = torch.empty((prm.rgb_rows, prm.rgb_cols), dtype=torch.float32).pin_memory().numpy()
+    band.bind_output(out)
+    for seed in (1, 2, 3, 4):  # frame 1 runs stream by stream, frame 2 is captured into a CUDA graph, 3 and 4 replay it
+        left, right = configs.pair(prm, seed=seed)
+        plain.compute(left, right)
+        out[:] = -7.0
+        band.compute(left, right)
+        got = band.get_ndarray(out=out)
+        assert got is out
+        ref = plain.get_ndarray()
+        assert np.array_equal(out.view(np.uint32), ref.view(np.uint32)), f"{int((out != ref).sum())} pixels differ"
+        for st in ("disp_wta", "disp_right", "disp_med", "depth"):
+            a, b = band.get_stage(st), plain.get_stage(st)
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), st
+        # other getters still work on a streamed frame
+        assert np.array_equal(band.get_ndarray().view(np.uint32), ref.view(np.uint32))
+        assert np.array_equal(band.get_cuda().torch().cpu().numpy().view(np.uint32), ref.view(np.uint32))
+    band.bind_output(None)
+    band.compute(left, right)
+    assert np.array_equal(band.get_ndarray().view(np.uint32), ref.view(np.uint32))
+
+
 @pytest.mark.parametrize("bbox", [(8, 4, 64, 40), (0, 0, 96, 64), (31, 23, 33, 37), (60, 30, 36, 34)])
 def test_small_bbox_vs_oracle(native, oracle, bbox):
     prm = configs.params("small")
