@@ -214,8 +214,8 @@ template <bool RGBA, int MINB>
 __global__ void __launch_bounds__(F7_NT, MINB) front7_kernel(const FrontParams p) {
   __shared__ __align__(16) uint32_t win[1][F7_WH][F7_WB / 4];
   const int tid = threadIdx.x;
-  const int n = blockIdx.z >> 1;
-  const int img = blockIdx.z & 1;
+  const int n = p.only_image < 0 ? blockIdx.z >> 1 : blockIdx.z;
+  const int img = p.only_image < 0 ? blockIdx.z & 1 : p.only_image;
   const int X0 = blockIdx.x * F7_TW, Y0 = blockIdx.y * F7_TH;
   if (p.canvas) { // grid-stride fill of the registration canvas (initRgbDepth, camera.cu:170-177)
     const size_t nthr = (size_t)gridDim.x * gridDim.y * gridDim.z * F7_NT;
@@ -332,11 +332,12 @@ __global__ void __launch_bounds__(F7_NT, MINB) front7_kernel(const FrontParams p
 cudaError_t launch_front(const FrontParams &p, cudaStream_t st) {
   if (p.N > 32767) return cudaErrorInvalidValue;
   if (p.cw == 7 && p.ch == 7) {
-    const dim3 grid((p.cols + F7_TW - 1) / F7_TW, (p.rows + F7_TH - 1) / F7_TH, 2 * p.N);
+    const dim3 grid((p.cols + F7_TW - 1) / F7_TW, (p.rows + F7_TH - 1) / F7_TH, (p.only_image < 0 ? 2 : 1) * p.N);
     if (p.left_rgba) front7_kernel<true, 4><<<grid, F7_NT, 0, st>>>(p);
     else front7_kernel<false, 4><<<grid, F7_NT, 0, st>>>(p);
     return cudaGetLastError();
   }
+  if (p.only_image >= 0) return cudaErrorInvalidValue; // per-image launches: 7x7 census path only
   const dim3 grid((p.cols + FT - 1) / FT, (p.rows + FT - 1) / FT, p.N);
   const dim3 block(FT, FTY);
   const size_t smem = 2 * (size_t)(FT + p.cw - 1) * (FT + p.ch - 1);

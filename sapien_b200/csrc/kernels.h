@@ -29,6 +29,9 @@ struct FrontParams {
   float *canvas;
   size_t canvas_n;
   float canvas_fill;
+  // -1: both images in one launch; 0 / 1: only the left / right image (7x7 census path), so that the
+  // left image can be processed while the right one is still being uploaded
+  int only_image;
 };
 cudaError_t launch_front(const FrontParams &p, cudaStream_t stream);
 
