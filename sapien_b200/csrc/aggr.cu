@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(128) aggr_kernel(const __grid_constant__ AggrA
 // Hand-over through two full/empty mbarrier pairs, so the serial SGM chain never waits for the
 // winner-takes-all arithmetic.
 template <int NR, bool PARTIAL, bool DBG, int K, int NCH>
-__global__ void __launch_bounds__(320) aggr_wta_kernel(const __grid_constant__ AggrArgs a) {
+__global__ void __launch_bounds__(512) aggr_wta_kernel(const __grid_constant__ AggrArgs a) {
   constexpr int DPL = 2 * NR;
   constexpr int NS = 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -684,10 +684,13 @@ static cudaError_t launch_one(const AggrArgs &a_in, cudaStream_t st) {
   cudaError_t e;
   if constexpr (MODE == 2) {
     auto k = aggr_wta_kernel<NR, PARTIAL, DBG, K, NCH>;
-    // rows per block: enough for one resident wave with one block per SM when shared memory allows (<= 5)
+    // rows per block: enough for one resident wave with one block per SM when shared memory allows
+    // (<= 5 rows in the latency-bound single-frame regime; up to 8 with the 2-slot rings of the
+    // batched regime, where rows are plentiful and more resident rows hide more latency)
     long ppb = (npaths + a.nsm - 1) / a.nsm;
     const long fit = (long)((227 * 1024) / smem);
-    if (ppb > 5) ppb = 5;
+    const long cap = NCHO == 2 ? 8 : 5;
+    if (ppb > cap) ppb = cap;
     if (ppb > fit) ppb = fit;
     if (ppb < 1) ppb = 1;
     const size_t bsmem = smem * (size_t)ppb;
@@ -720,7 +723,7 @@ template <int MODE, int NCHO = 0> static cudaError_t dispatch(const AggrArgs &a,
   case NRV:                                                                                       \
     if (MODE == 0) return partial ? launch_one<NRV, MODE, true, false, NCHO>(a, st) : launch_one<NRV, MODE, false, false, NCHO>(a, st); \
     if (dbg) return partial ? launch_one<NRV, MODE, true, true>(a, st) : launch_one<NRV, MODE, false, true>(a, st);  \
-    return partial ? launch_one<NRV, MODE, true, false>(a, st) : launch_one<NRV, MODE, false, false>(a, st);
+    return partial ? launch_one<NRV, MODE, true, false, (MODE == 2 ? NCHO : 0)>(a, st) : launch_one<NRV, MODE, false, false, (MODE == 2 ? NCHO : 0)>(a, st);
   switch (nr) {
     SSB_CASE(1) SSB_CASE(2) SSB_CASE(4) SSB_CASE(8) SSB_CASE(16)
   }
@@ -816,6 +819,9 @@ cudaError_t launch_aggr_final(const AggrBuffers &b, int N, int rows, int cols, i
     if ((seg_end[i] & 31) || seg_end[i] <= (i ? seg_end[i - 1] : 0) || seg_end[i] >= cols) return cudaErrorInvalidValue;
     w.seg_end[i] = seg_end[i];
   }
+  // more rows than one wave of 5-row blocks can hold: throughput regime (see launch_one)
+  static const bool no_batched = getenv("SSB_FINAL_NO_BATCHED") != nullptr;
+  if (!no_batched && (long)N * rows > 5L * w.nsm) return dispatch<2, 2>(w, stream);
   return dispatch<2>(w, stream);
 }
 
