@@ -384,9 +384,9 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
       const bool last = s == nseg;
       if (last) { // the columns behind the last progress point: after the pass itself
         CK(cudaStreamWaitEvent(e->aux, e->ev_seg[1], 0));
-        pp.wait_ctr = nullptr; pp.wait_target = 0;
-      } else { // the band's blocks start now and wait until every row has passed seg_end[s]
-        pp.wait_ctr = e->progress + s; pp.wait_target = (uint32_t)c.batch * (uint32_t)rows;
+      } else { // a one-warp gate holds the helper stream until every row has passed seg_end[s]
+        CK(launch_gate(e->progress + s, (uint32_t)c.batch * (uint32_t)rows, e->aux));
+        ++launches;
       }
       // LR check reads dispR up to D-1 columns back (final D-1 columns behind the pass), the median H columns ahead
       const int xb = last ? cols : std::max(xa, ((seg_end[s] - D - H) / 32) * 32);

@@ -105,12 +105,10 @@ struct PostParams {
   // (ua % 4 == 0); the bands of one frame are launched left to right on one stream and replace the
   // whole-frame call (the canvas is prefilled by the front-end).  No ROI mode.
   int xa, xb, ua, ub;
-  // optional: the band's kernels start early and their blocks wait (one polling thread each, with
-  // back-off) until *wait_ctr >= wait_target -- the progress counter of the final aggregation pass
-  const uint32_t *wait_ctr;
-  uint32_t wait_target;
 };
 cudaError_t launch_post(const PostParams &p, cudaStream_t stream, int *launches);
+// one-warp kernel that returns once *ctr >= target (the progress counters of launch_aggr_final)
+cudaError_t launch_gate(const uint32_t *ctr, uint32_t target, cudaStream_t stream);
 
 cudaError_t launch_point_cloud(const float *depth, const float *rgba, float *pc, int N, int rows,
                                int cols, float fx, float fy, float skew, float cx, float cy,

@@ -72,18 +72,23 @@ __device__ __forceinline__ void depth_and_splat(const PostParams &p, size_t n, s
   }
 }
 
-// Blocks of a band launched ahead of its data: wait for the producer's progress counter.
-__device__ __forceinline__ void wait_progress(const PostParams &p, bool leader) {
-  if (!p.wait_ctr) return;
-  if (leader) {
+// Gate of a column band: ONE warp waits (with back-off) until the final aggregation pass has bumped
+// its progress counter to `target`; the band's kernels follow in stream order.  A single waiting warp
+// cannot keep the pass's own blocks off an SM, whatever order the hardware starts the kernels in
+// (band kernels whose every block polled could: 8 such blocks fill the thread slots of an SM).
+__global__ void gate_kernel(const uint32_t *ctr, uint32_t target) {
+  if (threadIdx.x == 0) {
     unsigned v;
     for (;;) {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.wait_ctr) : "memory");
-      if (v >= p.wait_target) break;
-      __nanosleep(1000);
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if (v >= target) break;
+      __nanosleep(500);
     }
   }
-  __syncthreads();
+}
+cudaError_t launch_gate(const uint32_t *ctr, uint32_t target, cudaStream_t st) {
+  gate_kernel<<<1, 32, 0, st>>>(ctr, target);
+  return cudaGetLastError();
 }
 
 // FUSE: no ROI -> the matched image is the full image, so depth + splat run in the same thread.
@@ -96,7 +101,6 @@ __global__ void __launch_bounds__(PT_X *PT_Y) lr_median_kernel(const PostParams 
   const int x0 = p.xa + blockIdx.x * PT_X, y0 = blockIdx.y * PT_Y; // columns [xa, xb) of every row
   const size_t img = (size_t)n * p.rows * p.cols;
   const int tid = threadIdx.y * PT_X + threadIdx.x;
-  wait_progress(p, tid == 0);
   // Tile load in straight-line phases (left disparities, then the dependent right-disparity
   // gathers) so that the loads of all rounds are in flight together.
   constexpr int NT = PT_X * PT_Y, NEL = WR * WC, NRND = (NEL + NT - 1) / NT;
@@ -181,7 +185,6 @@ __global__ void __launch_bounds__(256) depth_splat_kernel(const PostParams p) { 
 // out(x,y) = min over the 2x2 block (x..x+1, y..y+1) of the inputs that are < maxDepth.
 // 2-D grid (no index divisions), 4 pixels per thread.
 __global__ void __launch_bounds__(128) dilate_range_kernel(const PostParams p) {
-  wait_progress(p, threadIdx.x == 0);
   const int x4 = p.ua + (blockIdx.x * blockDim.x + threadIdx.x) * 4; // columns [ua, ub): ua % 4 == 0
   const int y = blockIdx.y;
   if (x4 >= p.ub) return;

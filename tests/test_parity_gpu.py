@@ -140,6 +140,29 @@ def test_banded_output_is_bit_identical(native, cfg, over):
     assert np.array_equal(band.get_ndarray().view(np.uint32), ref.view(np.uint32))
 
 
+def test_banded_output_batched_multi_wave(native):
+    """Batched engine whose final pass needs more than one wave of blocks (6 x 256 rows, 8 rows per block): the band
+    kernels are gated by ONE waiting warp, so they cannot starve the pass they wait for."""
+    import torch
+
+    prm = configs.params("C4")
+    n = 6
+    pairs = [configs.pair(prm, seed=40 + i) for i in range(n)]
+    left = np.stack([p[0] for p in pairs])
+    right = np.stack([p[1] for p in pairs])
+    plain = make_engine(native, prm, batch=n)
+    band = make_engine(native, prm, batch=n)
+    out = torch.empty((n, prm.rgb_rows, prm.rgb_cols), dtype=torch.float32).pin_memory().numpy()
+    band.bind_output(out)
+    for _ in range(3):
+        plain.compute(left, right)
+        out[:] = -3.0
+        band.compute(left, right)
+        band.get_ndarray(out=out)
+        ref = plain.get_ndarray()
+        assert np.array_equal(out.view(np.uint32), ref.reshape(out.shape).view(np.uint32))
+
+
 @pytest.mark.parametrize("bbox", [(8, 4, 64, 40), (0, 0, 96, 64), (31, 23, 33, 37), (60, 30, 36, 34)])
 def test_small_bbox_vs_oracle(native, oracle, bbox):
     prm = configs.params("small")
