@@ -41,14 +41,18 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
         if not os.path.exists(nvcc):
             raise RuntimeError("nvcc not found and no prebuilt libss_b200.so")
-        objs = []
-        for s in CU_SOURCES:  # separate objects: only changed sources recompile
+        from concurrent.futures import ThreadPoolExecutor
+
+        objs, jobs = [], []
+        for s in CU_SOURCES:  # separate objects: only changed sources recompile, and they compile side by side
             o = os.path.join(CSRC, s[:-3] + ".o")
             if force or _stale(o, [os.path.join(CSRC, s)] + deps[len(srcs):]):
                 if verbose:
                     print("nvcc", s, file=sys.stderr)
-                _run([nvcc, *NVCC_FLAGS, "-c", s, "-o", o])
+                jobs.append([nvcc, *NVCC_FLAGS, "-c", s, "-o", o])
             objs.append(o)
+        with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as pool:
+            list(pool.map(_run, jobs))
         _run([nvcc, "-shared", "-o", LIB, *objs])
     return LIB
 
