@@ -194,35 +194,41 @@ def run_ours(args, rank, world, local):
         from sapien_b200 import synth
 
         rgba = torch.from_numpy(synth.make_rgb(prm.rgb_rows, prm.rgb_cols, 0)).cuda()
-    stream = torch.cuda.Stream()
+    # Frames are enqueued back to back on the ENGINE's stream (inputs are resident and ready: no caller stream
+    # to order against), and the CUDA events that time them are recorded on that same stream.
+    stream = torch.cuda.ExternalStream(eng.cuda_stream, device=torch.device("cuda", local))
     bb = (True, *bbox_t) if bbox_t else (False, 0, 0, 0, 0)
 
     def step(i):
         l, r = dev_sets[i % n_sets]
-        eng.compute(l, r, *bb, stream=stream.cuda_stream, sync=False)
+        eng.compute(l, r, *bb, sync=False)
         if pc:
             eng.get_rgb_point_cloud_cuda(rgba)
 
-    with torch.cuda.stream(stream):
-        for i in range(args.warmup):
-            step(i)
-        stream.synchronize()
-        barrier(world)
-        eng.set_profiling(True)
-        eng.get_stage_times()
-        sampler = ClockSampler(local)
-        sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for i in range(args.steps):
-            step(i)
-        e1.record(stream)
-        stream.synchronize()
-        barrier(world)
-        ms = e0.elapsed_time(e1)
-        clocks = sampler.stop()
-        stages = dict(eng.get_stage_times())
-        eng.set_profiling(False)
+    torch.cuda.synchronize()
+    for i in range(args.warmup):
+        step(i)
+    stream.synchronize()
+    barrier(world)
+    eng.set_profiling(True)
+    eng.get_stage_times()
+    for i in range(min(args.steps, 20)):  # per-kernel stage times: a separate, profiled run (event marks between the stages)
+        step(i)
+    stream.synchronize()
+    stages = dict(eng.get_stage_times())
+    eng.set_profiling(False)
+    barrier(world)
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    stream.synchronize()
+    barrier(world)
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
     launches = eng.get_launches_per_compute() + (1 if pc else 0)
     ms = max_over_ranks(ms, world)
     frames = batch * args.steps * world
@@ -285,6 +291,7 @@ def run_ours(args, rank, world, local):
         "config": {"workload": f"{args.workload}: {desc}", "batch_per_gpu": batch, "input": "device float32 RGBA pairs (reference CUDA input format)",
                    "l2": f"{n_sets} distinct input sets rotate; per-step intermediate traffic (3 u16 volumes = {3 * V / 1e6:.0f} MB) exceeds the 126 MB L2" if 3 * V > 126e6
                    else f"{n_sets} distinct input sets rotate; volumes of one batch = {3 * V / 1e6:.0f} MB",
+                   "pipelining": "frames enqueued back to back on the engine's stream; the front-end of frame k+1 (helper stream) overlaps the final pass / post-processing of frame k",
                    "parallelism": f"env-sharded x{world}, no collective"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches * args.steps,
         "roofline": roofline,

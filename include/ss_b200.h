@@ -103,6 +103,9 @@ int ss_get_output_shape(const ss_engine *e, uint32_t *rows, uint32_t *cols);
 int ss_get_input_shape(const ss_engine *e, uint32_t *rows, uint32_t *cols);
 /* E:66 / C:384-388 */
 int ss_get_device(const ss_engine *e, int32_t *device);
+/* Extension: the engine's own stream (a cudaStream_t), e.g. to record events around a run of frames
+ * enqueued with stream = 0.  The reference keeps its three streams private (core.h:95-97). */
+int ss_get_stream(const ss_engine *e, void **stream);
 
 /* E:63 getMat2d / P:101: depth float32 [batch][out_rows][out_cols] copied to `out`. */
 int ss_get_depth_host(ss_engine *e, float *out, size_t capacity_bytes);

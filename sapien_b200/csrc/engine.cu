@@ -94,6 +94,8 @@ struct ss_engine {
   uint16_t *dbgL0 = nullptr, *dbgL3 = nullptr, *dbgLAll = nullptr;
   float *dispL = nullptr, *disp_lr = nullptr, *disp_med = nullptr, *disp_full = nullptr;
   float *depth = nullptr, *canvas = nullptr, *out = nullptr, *pc = nullptr, *rgbpc = nullptr;
+  float *canvas_pair[2] = {nullptr, nullptr}; // splat canvases of even / odd frames (see the front-end launch)
+  cudaEvent_t ev_cost = nullptr, ev_front = nullptr; // previous frame past its HBM-bound passes / front-end of this frame done
   uint16_t *dispR = nullptr;
   int wave = 1;
   bool computed = false;
@@ -154,6 +156,8 @@ int create_impl(ss_engine *e, const float *mapLx, const float *mapLy, const floa
   for (auto &ev : e->ev_seg) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto &ev : e->ev_band) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&e->ev_copied, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&e->ev_cost, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&e->ev_front, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
   const size_t fsz = e->fsz(), N = (size_t)c.batch;
@@ -223,7 +227,9 @@ int create_impl(ss_engine *e, const float *mapLx, const float *mapLy, const floa
   if ((r = e->alloc(&e->disp_med, N * fsz))) return r;
   if ((r = e->alloc(&e->disp_full, N * fsz))) return r;
   if ((r = e->alloc(&e->depth, N * fsz))) return r;
-  if (c.registration && (r = e->alloc(&e->canvas, N * e->rsz()))) return r;
+  if (c.registration && (r = e->alloc(&e->canvas_pair[0], N * e->rsz()))) return r;
+  if (c.registration && (r = e->alloc(&e->canvas_pair[1], N * e->rsz()))) return r;
+  e->canvas = e->canvas_pair[0];
   if ((r = e->alloc(&e->out, N * e->rsz()))) return r;
   if ((r = e->alloc(&e->pc, N * e->rsz() * 3))) return r;
   if ((r = e->alloc(&e->rgbpc, N * e->rsz() * 6))) return r;
@@ -262,6 +268,7 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
   }
   e->mark("begin");
 
+  if (c.registration) e->canvas = e->canvas_pair[e->frame & 1];
   const int D = c.max_disp;
   const int P1 = c.p1 * c.bf_width * c.bf_height, P2 = c.p2 * c.bf_width * c.bf_height; // core.cu:670-671
   const int cmax = census_bits(c.census_width, c.census_height) * c.bf_width * c.bf_height;
@@ -321,6 +328,19 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
       CK(cudaEventRecord(e->ev[1], e->aux));
       CK(cudaStreamWaitEvent(st, e->ev[1], 0));
       ++launches;
+    } else if (c.batch <= e->wave) {
+      // Device inputs, one wave: the front-end runs on the helper stream and only waits until the previous
+      // frame is past its aggregation, so with frames enqueued back to back it overlaps the previous
+      // frame's post-processing (both are small latency-bound kernels: 24 us hidden, C1 1880 -> 1996
+      // frames/s).  Released earlier it costs more than it hides: after the cost kernel -- the last reader
+      // of the census buffers -- it takes bandwidth and the L2 lines the bottom->top pass counts on
+      // (138 -> 166 us); after that pass it slows the final one (104 -> 123 us).  It fills the OTHER splat
+      // canvas (the previous frame's dilation may still be reading its own).
+      if (user && user != st) CK(cudaStreamWaitEvent(e->aux, e->ev_in, 0));
+      CK(cudaStreamWaitEvent(e->aux, e->ev_cost, 0)); // (first frame: never recorded, no-op)
+      CK(launch_front(fp, e->aux));
+      CK(cudaEventRecord(e->ev_front, e->aux));
+      CK(cudaStreamWaitEvent(st, e->ev_front, 0));
     } else {
       CK(launch_front(fp, st));
     }
@@ -335,16 +355,20 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
     if (fast) {
       if (!c.keep_stages) { ab.dbgL0 = ab.dbgL3 = ab.dbgLAll = nullptr; }
       AggrMarks am{[](void *ctx, const char *name) { static_cast<ss_engine *>(ctx)->mark(name); }, e};
-      if (banded) { // the final pass follows below, with its progress counters
-        CK(launch_aggr_passes(ab, wn, rows, cols, D, P1, P2, c.uniq_ratio, st, e->aux, e->ev, e->profiling ? &am : nullptr));
-        launches += 3;
-      } else {
-        CK(launch_aggr_wta(ab, wn, rows, cols, D, P1, P2, c.uniq_ratio, st, e->aux, e->ev, e->profiling ? &am : nullptr));
-        launches += 4;
+      CK(launch_aggr_passes(ab, wn, rows, cols, D, P1, P2, c.uniq_ratio, st, e->aux, e->ev, e->profiling ? &am : nullptr));
+      launches += 3;
+      if (!banded) { // (banded: the final pass follows below, with its progress counters)
+        CK(launch_aggr_final(ab, wn, rows, cols, D, P1, P2, c.uniq_ratio, st, nullptr, 0, nullptr));
+        e->mark("aggr_right_wta");
+        launches += 1;
       }
+      // from here on the next frame's front-end may run (see above): what is left of this frame are the
+      // small post-processing kernels (banded: the final pass as well)
+      if (c.batch <= e->wave) CK(cudaEventRecord(e->ev_cost, st));
       launches += 2;
     } else {
       CK(launch_aggr_wta_generic(ab, nullptr, wn, rows, cols, D, P1, P2, c.uniq_ratio, st));
+      if (c.batch <= e->wave) CK(cudaEventRecord(e->ev_cost, st));
       launches += 8;
     }
     if (!fast) e->mark("aggr_wta_generic");
@@ -479,6 +503,8 @@ int ss_destroy(ss_engine *e) {
   for (auto ev : e->ev_seg) if (ev) cudaEventDestroy(ev);
   for (auto ev : e->ev_band) if (ev) cudaEventDestroy(ev);
   if (e->ev_copied) cudaEventDestroy(e->ev_copied);
+  if (e->ev_cost) cudaEventDestroy(e->ev_cost);
+  if (e->ev_front) cudaEventDestroy(e->ev_front);
   if (e->cpy) { cudaStreamSynchronize(e->cpy); cudaStreamDestroy(e->cpy); }
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_out) cudaEventDestroy(e->ev_out);
@@ -530,6 +556,11 @@ int ss_get_output_shape(const ss_engine *e, uint32_t *rows, uint32_t *cols) {
 int ss_get_input_shape(const ss_engine *e, uint32_t *rows, uint32_t *cols) {
   if (!e || !rows || !cols) return fail(SS_ERR_INVALID, "null argument");
   *rows = e->cfg.rows; *cols = e->cfg.cols;
+  return SS_OK;
+}
+int ss_get_stream(const ss_engine *e, void **stream) {
+  if (!e || !stream) return fail(SS_ERR_INVALID, "null argument");
+  *stream = e->stream;
   return SS_OK;
 }
 int ss_get_device(const ss_engine *e, int32_t *device) {

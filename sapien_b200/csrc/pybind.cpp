@@ -309,6 +309,7 @@ public:
   uint32_t outCols() const { return ocols_; }
   int device() const { return device_; }
   int batch() const { return batch_; }
+  uintptr_t cudaStream() const { void *st = nullptr; check(ss_get_stream(e_, &st)); return reinterpret_cast<uintptr_t>(st); }
 
 private:
   void checkHostShape(const U8 &l, const U8 &r) {
@@ -434,5 +435,6 @@ PYBIND11_MODULE(_simsense_b200, m) {
       .def_property_readonly("output_rows", &E::outRows)
       .def_property_readonly("output_cols", &E::outCols)
       .def_property_readonly("cuda_id", &E::device)
-      .def_property_readonly("batch", &E::batch);
+      .def_property_readonly("batch", &E::batch)
+      .def_property_readonly("cuda_stream", &E::cudaStream);
 }

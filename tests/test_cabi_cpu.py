@@ -57,7 +57,7 @@ def good_config(**over):
 def test_header_declares_the_expected_surface():
     fns = declared_functions()
     for must in ("ss_create", "ss_destroy", "ss_compute_host_u8", "ss_compute_device_rgba_f32", "ss_compute_device_u8",
-                 "ss_get_depth_host", "ss_bind_output_host", "ss_get_depth_device", "ss_get_point_cloud_host", "ss_get_point_cloud_device",
+                 "ss_get_depth_host", "ss_bind_output_host", "ss_get_stream", "ss_get_depth_device", "ss_get_point_cloud_host", "ss_get_point_cloud_device",
                  "ss_get_rgb_point_cloud_host", "ss_get_rgb_point_cloud_device", "ss_set_ir_noise_parameters",
                  "ss_set_penalties", "ss_set_census_window_size", "ss_set_matching_block_size",
                  "ss_set_uniqueness_ratio", "ss_set_lr_max_diff", "ss_last_error"):
