@@ -163,6 +163,56 @@ def test_banded_output_batched_multi_wave(native):
         assert np.array_equal(out.view(np.uint32), ref.reshape(out.shape).view(np.uint32))
 
 
+@pytest.mark.parametrize("cfg", ["C4", "C1"])
+def test_back_to_back_frames_overlap_without_corruption(native, cfg):
+    """Frames enqueued back to back on the engine's stream: the front-end of frame k+1 runs on the helper stream while
+    frame k is still post-processing (second splat canvas).  Every frame's depth map, snapshotted on the engine stream
+    right behind its compute, must equal the map of the same inputs computed alone -- also when host-input, banded and
+    ROI frames are mixed into the sequence."""
+    import torch
+
+    prm = configs.params(cfg)
+    n = 6
+    pairs = [configs.pair(prm, seed=70 + i) for i in range(n)]
+    solo = make_engine(native, prm)
+    want = []
+    for l, r in pairs:
+        solo.compute(l, r)
+        want.append(solo.get_ndarray())
+    eng = make_engine(native, prm)
+    es = torch.cuda.ExternalStream(eng.cuda_stream)
+    dl = [torch.from_numpy(l).cuda() for l, _ in pairs]
+    dr = [torch.from_numpy(r).cuda() for _, r in pairs]
+    torch.cuda.synchronize()
+    snaps = [torch.empty((prm.rgb_rows, prm.rgb_cols), dtype=torch.float32, device="cuda") for _ in range(n)]
+    for rep in range(2):
+        for i in range(n):
+            eng.compute(dl[i], dr[i], sync=False)
+            with torch.cuda.stream(es):
+                snaps[i].copy_(eng.get_cuda().torch(), non_blocking=True)
+        es.synchronize()
+        for i in range(n):
+            assert np.array_equal(snaps[i].cpu().numpy().view(np.uint32), want[i].view(np.uint32)), f"frame {i} (rep {rep})"
+    # mixed sequence on one engine: device async, host, host banded, ROI, device async again
+    out = torch.empty((prm.rgb_rows, prm.rgb_cols), dtype=torch.float32).pin_memory().numpy()
+    eng.compute(dl[0], dr[0], sync=False)
+    eng.compute(*pairs[1])
+    assert np.array_equal(eng.get_ndarray().view(np.uint32), want[1].view(np.uint32))
+    eng.bind_output(out)
+    eng.compute(dl[2], dr[2], sync=False)
+    eng.compute(*pairs[3])
+    eng.get_ndarray(out=out)
+    assert np.array_equal(out.view(np.uint32), want[3].view(np.uint32))
+    eng.compute(*pairs[4], True, 16, 8, prm.cols // 2, prm.rows // 2)
+    eng.compute(dl[5], dr[5], sync=False)
+    eng.compute(*pairs[0])
+    eng.get_ndarray(out=out)
+    assert np.array_equal(out.view(np.uint32), want[0].view(np.uint32))
+    eng.bind_output(None)
+    eng.compute(dl[5], dr[5])
+    assert np.array_equal(eng.get_ndarray().view(np.uint32), want[5].view(np.uint32))
+
+
 @pytest.mark.parametrize("bbox", [(8, 4, 64, 40), (0, 0, 96, 64), (31, 23, 33, 37), (60, 30, 36, 34)])
 def test_small_bbox_vs_oracle(native, oracle, bbox):
     prm = configs.params("small")
