@@ -13,12 +13,14 @@
 //    per-lane byte-permute selector that folds the d=0 / d=D-1 border rule into the same PRMT;
 //    the running minimum is vmin + half-swap + ONE redux.sync (CREDUX) that already returns
 //    m|m<<16; the min/add chain is Blackwell DPX (VIADDMNMX.U16x2, VIMNMX.U16x2, VIMNMX3.U16x2);
-//  * the cost volume (and the partial sums of earlier passes) are streamed into shared memory by
-//    the bulk-copy engine (cp.async.bulk / UBLKCP, completion on an mbarrier) in chunks of K path
-//    steps, NCH chunks deep per warp: one 4 KB request per chunk for horizontal paths, K row
-//    pieces issued by K lanes at once for vertical ones.  No per-step address arithmetic, no
+//  * the cost volume (and the partial sums of earlier passes) are streamed into shared memory by the
+//    copy engines, completion on an mbarrier, in chunks of K path steps, NCH chunks deep per warp:
+//    horizontal paths take one 4 KB bulk copy per chunk (cp.async.bulk / UBLKCP); vertical paths take
+//    ONE 2-D tensor copy per stream and chunk (cp.async.bulk.tensor / UTMALDG, box = K rows x one
+//    pixel's D costs, a CUtensorMap per volume in the kernel arguments) when a pixel's costs are whole
+//    128-byte lines, else K bulk row pieces issued by K lanes.  No per-step address arithmetic, no
 //    LDGSTS issue cost; a warp keeps (NCH-1)*K*D*2 bytes per stream in flight;
-//  * pass order is  right->left  ->  top->bottom  ->  bottom->top (+L1+L2)  ->  left->right.
+//  * pass order is  right->left || top->bottom (two streams)  ->  bottom->top (+L1+L2)  ->  left->right.
 //    The last pass forms LAll(y,x,:) = (L0+L1+L2+L3)/4 in registers.  Per step it only records the
 //    packed (min,argmin) key and advances the right-disparity recurrence along the diagonal,
 //    T_x(d) = min(T_{x-1}(d-1), LAll(x,d)); the LAll row goes to a 32-pixel shared tile and every 32
