@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(512) aggr_wta_kernel(const __grid_constant__ A
   const uint32_t barFull = bar0 + 8 * NCH, barEmpty = barFull + 8 * WTA_TILES;
   if (role == 0 && lane == 0) {
 #pragma unroll
-    for (int i = 0; i < NCH + 2 * WTA_TILES; ++i) mbar_init(bar0 + 8 * i, 1);
+    for (int i = 0; i < NCH + 2 * WTA_TILES; ++i) mbar_init(bar0 + 8 * i, i < NCH ? 1 : 32); // tile hand-over: every lane arrives
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -485,12 +485,9 @@ __global__ void __launch_bounds__(512) aggr_wta_kernel(const __grid_constant__ A
         for (int k = 0; k < kc; ++k) { step(pc, trow); pc += PIECE; trow += TP; }
       }
       const int done = s0 + kc;
-      if ((done & 31) == 0 || done == steps) { // tile complete: publish it
-        __syncwarp();
-        if (lane == 0) {
-          const uint32_t bar = barFull + 8 * (((done - 1) >> 5) % WTA_TILES);
-          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-        }
+      if ((done & 31) == 0 || done == steps) { // tile complete: publish it (every lane releases its own stores)
+        const uint32_t bar = barFull + 8 * (((done - 1) >> 5) % WTA_TILES);
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
       }
       if (++slot == NCH) { slot = 0; parity ^= 1; }
     }
@@ -608,7 +605,7 @@ __global__ void __launch_bounds__(512) aggr_wta_kernel(const __grid_constant__ A
 #pragma unroll 8
       for (int k = 0; k < 32; ++k) { // the next row's load is in flight while this one is processed
         trow += TP;
-        load_row(trow, nxt); // k == 31 reads the row after the tile: inside the tile ring or gk/rb area
+        if (k < 31) load_row(trow, nxt); // (the row after the tile belongs to the producer: never touched)
         cstep(cur, k);
 #pragma unroll
         for (int r = 0; r < NR; ++r) cur[r] = nxt[r];
@@ -617,11 +614,11 @@ __global__ void __launch_bounds__(512) aggr_wta_kernel(const __grid_constant__ A
       for (int k = 0; k < cnt; ++k) {
         cstep(cur, k);
         trow += TP;
-        load_row(trow, cur);
+        if (k + 1 < cnt) load_row(trow, cur);
       }
     }
     tile_phase(tbase, t0, cnt);
-    if (lane == 0) {
+    {
       const uint32_t bar = barEmpty + 8 * ts;
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
     }
