@@ -4,6 +4,8 @@
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+nxt = next((i for i, r in enumerate(rows) if i > hdr_i and r and r[0] == "Kernel Name"), len(rows))
+rows = rows[:nxt]  # first kernel instance only
 hdr = rows[hdr_i]
 col = {n: i for i, n in enumerate(hdr)}
 stalls = [n for n in hdr if n.startswith("stall_") and "Not Issued" not in n]
