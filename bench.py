@@ -9,10 +9,15 @@
 One "step" = one pass of the hot path (DepthSensorEngine compute: front-end, cost volume, 4-path
 SGM, WTA, LR, median, depth, registration) over one synthetic batch.  `value` is measured with the
 inputs resident in HBM (device RGBA float32, the reference's CUDA input format), CUDA-event timed
-on the stream the work is ordered on; `e2e` goes through the public Python API with pinned HOST
-buffers, uploads and the depth read-back inside the timed region.  N>1: one process per GPU
-(torchrun), the same per-GPU workload on every rank (environments/frames are independent: no
-collective on the data path), barrier + max-over-ranks timing, `scaling` = weak.
+on the stream the work is ordered on; `e2e` goes through the public Python API with HOST
+buffers, uploads and the depth read-back inside the timed region (two figures: the extension path
+with a bound pinned output, and the strict reference signature compute(l, r) + get_ndarray()).
+N>1: one process per GPU (torchrun), the same per-GPU workload on every rank (environments/frames
+are independent: no collective on the data path), barrier + max-over-ranks timing, `scaling` =
+weak.  The same line carries a `batched` block measured in the same process: north_star's batched,
+sharded workloads -- C4 (1 024 envs x 256x256, D=64) split env_range(1024, rank, world) through
+ShardedStereoDepth (STRONG scaling: 1024/N envs per rank) with the optional NCCL all-gather timed
+separately, and the C5 sweep (1920x1080, D=256, 4-frame batches, frames split contiguously).
 """
 from __future__ import annotations
 
@@ -50,6 +55,10 @@ def parse():
     ap.add_argument("--workload", default="C1", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the env batch of the workload (per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batched", action="store_true", help="skip the batched block (C4 1024-env shard + C5 sweep)")
+    ap.add_argument("--c4-envs", type=int, default=1024)
+    ap.add_argument("--c5-frames", type=int, default=256, help="frames of the C5 sweep over all ranks (north_star: 4096)")
+    ap.add_argument("--pipelines", type=int, default=0, help="engines per rank for the batched block (0 = default per workload)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -130,7 +139,9 @@ def dist_setup(n_gpus):
     if world > 1:
         import torch.distributed as dist
 
-        os.environ["NCCL_DEBUG"] = os.environ.get("SSB_NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: ONE JSON line
+        # NCCL's INFO log (communicator size, transports) goes to STDERR: stdout carries ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return rank, world, local
 
@@ -143,6 +154,17 @@ def barrier(world):
 
         dist.barrier()
     torch.cuda.synchronize()
+
+
+def sum_over_ranks(v: float, world) -> float:
+    if world == 1:
+        return v
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([v], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
 
 
 def max_over_ranks(v: float, world) -> float:
@@ -191,6 +213,192 @@ def cpu_baseline(prm, bbox, seconds, torch_threads=None):
             "sample": f"{n} frames of the workload, one frame at a time, OpenMP over rows/columns on {cores} threads (after 1 warm-up frame)"}
 
 
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def shared_config(args, desc, batch, world):
+    """`config` is identical in both arms (what differs between the arms is in `arm`)."""
+    return {"workload": f"{args.workload}: {desc}", "batch_per_gpu": batch, "input": "device float32 RGBA pairs (the reference's CUDA input format)",
+            "l2": "8 distinct input sets rotate; per-step intermediate traffic (u16 cost volumes) exceeds the 126 MB L2",
+            "parallelism": f"env-sharded x{world}, no collective"}
+
+
+def c4_inputs(prm, start, stop, n_sets, torch):
+    """Device RGBA batches [n_local,H,W,4] for envs [start, stop): env e uses seed e % 64 (shifted per set)."""
+    from sapien_b200 import synth
+
+    base = [synth.make_pair(prm.rows, prm.cols, prm.max_disp, s)[:2] for s in range(64)]
+    bl = torch.from_numpy(synth.to_rgba(np.stack([b[0] for b in base]))).cuda()
+    br = torch.from_numpy(synth.to_rgba(np.stack([b[1] for b in base]))).cuda()
+    sets = []
+    for k in range(n_sets):
+        idx = torch.tensor([(e + 7 * k) % 64 for e in range(start, stop)], device="cuda", dtype=torch.long)
+        sets.append((bl.index_select(0, idx).contiguous(), br.index_select(0, idx).contiguous()))
+    return sets
+
+
+def c5_inputs(prm, torch, n_base=8):
+    from sapien_b200 import synth
+
+    base = [synth.make_pair(prm.rows, prm.cols, prm.max_disp, s)[:2] for s in range(n_base)]
+    l = torch.from_numpy(synth.to_rgba(np.stack([b[0] for b in base]))).cuda()
+    r = torch.from_numpy(synth.to_rgba(np.stack([b[1] for b in base]))).cuda()
+    return l, r
+
+
+def time_sharded(sh, sets, steps, warmup, torch, world):
+    """`steps` passes of the local block through every pipeline of `sh`, device-timed: a timing stream opens the
+    region, every engine stream is ordered after it, and it closes behind all of them (max over ranks)."""
+    if not sh.engines:
+        barrier(world)
+        barrier(world)
+        return max_over_ranks(0.0, world)
+    ts = torch.cuda.Stream()
+    ext = [torch.cuda.ExternalStream(e.cuda_stream) for e in sh.engines]
+    for i in range(warmup):
+        sh.enqueue(*sets[i % len(sets)], inputs_ready=True)
+    sh.synchronize()
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ts)
+    for e in sh.engines:
+        e.wait_stream(ts.cuda_stream)
+    for i in range(steps):
+        sh.enqueue(*sets[i % len(sets)], inputs_ready=True)
+    for x in ext:
+        ts.wait_stream(x)
+    e1.record(ts)
+    ts.synchronize()
+    barrier(world)
+    return max_over_ranks(e0.elapsed_time(e1), world)
+
+
+def batched_ours(args, rank, world, local):
+    """north_star's batched, sharded workloads in the same process (see the module docstring)."""
+    import torch
+
+    from oracle import configs
+    from sapien_b200 import sharding
+
+    peak, _ = hbm_peak()
+    out = {}
+    steps = max(3, min(args.steps, 10))
+    # ---- C4: 1024 envs x 256x256, D=64, env_range(1024, rank, world) per rank: strong scaling ----
+    prm = configs.params("C4")
+    pipes = args.pipelines or 2
+    sh = sharding.ShardedStereoDepth(prm.engine_args(), args.c4_envs, rank, world, device=local, pipelines=pipes)
+    sets = c4_inputs(prm, sh.start, sh.stop, 2, torch)
+    ms = time_sharded(sh, sets, steps, 2, torch, world)
+    alg = configs.algorithmic_bytes(prm, rgba_input=True)
+    rate = args.c4_envs * steps / (ms / 1e3)
+    launches = sum(e.get_launches_per_compute() for e in sh.engines)
+    c4 = {"workload": f"C4: {args.c4_envs} envs x 256x256, 64 disp, split env_range({args.c4_envs}, rank, {world}) through ShardedStereoDepth",
+          "env_frames_per_s": rate, "envs_per_gpu": sh.local, "n_gpus": world, "scaling": "strong", "steps": steps, "ms_per_step": ms / steps,
+          "pipelines_per_gpu": len(sh.engines), "input": "device float32 RGBA [n,256,256,4] batches, 2 sets alternate (each 268 MB per image at 1024 envs)",
+          "algorithmic_bytes_per_env_frame": int(alg), "hbm_roofline_env_frames_per_s_per_gpu": peak * 1e9 / alg,
+          "frac_of_hbm_roofline": rate / world * alg / 1e9 / peak, "gpu_launches_per_step": launches}
+    # optional epilogue, outside the metric: NCCL all-gather of the depth maps for one host-side consumer
+    depth = sh.depth()
+    like = ((prm.rgb_rows, prm.rgb_cols), torch.float32, torch.device("cuda", local))
+    if world > 1:
+        full = sh.gather_depth(depth, like=like)
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(world)
+        g0.record()
+        for _ in range(3):
+            full = sh.gather_depth(depth, like=like)
+        g1.record()
+        torch.cuda.synchronize()
+        gms = max_over_ranks(g0.elapsed_time(g1) / 3, world)
+        nbytes = sh.local * prm.rgb_rows * prm.rgb_cols * 4
+        c4["gather"] = {"op": "all_gather_into_tensor (NCCL over NVLink), outside the metric", "bytes_per_rank": int(nbytes), "ms": gms,
+                        "algbw_gbs": nbytes * world / (gms * 1e-3) / 1e9, "result_shape": list(full.shape)}
+        del full
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        cb = cpu_baseline(prm, None, 2.0)
+        c4["cpu_oracle"] = {"env_frames_per_s": cb["value"], "cores": cb["cores"], "sample": cb["sample"]}
+    out["C4"] = c4
+    del sh, sets, depth
+    torch.cuda.empty_cache()
+    # ---- C5: 1920x1080, D=256, sweep of F frames in 4-frame batches, frames split contiguously over the ranks ----
+    prm = configs.params("C5")
+    f0, f1 = sharding.env_range(args.c5_frames, rank, world)
+    nb = (f1 - f0) // 4  # 4-frame batches of this rank
+    pipes5 = args.pipelines or 2
+    sh5 = sharding.ShardedStereoDepth(prm.engine_args(), 4, 0, 1, device=local, pipelines=pipes5)
+    bl, br = c5_inputs(prm, torch)
+    sets5 = [(bl[0:4], br[0:4]), (bl[4:8], br[4:8])]
+    frames = int(sum_over_ranks(4.0 * nb, world))  # (a remainder of < 4 frames per rank is left out)
+    ms5 = time_sharded(sh5, sets5, max(nb, 1), 1, torch, world) if frames else 0.0
+    alg5 = configs.algorithmic_bytes(prm, rgba_input=True)
+    rate5 = frames / (ms5 / 1e3) if ms5 else 0.0
+    out["C5"] = {"workload": f"C5: 1920x1080, 256 disp, sweep of {args.c5_frames} frames (north_star: 4096; --c5-frames), 4-frame batches, frames split contiguously over {world} ranks",
+                 "frames_per_s": rate5, "frames": frames, "frames_per_gpu": 4 * nb, "n_gpus": world, "scaling": "strong", "ms_total": ms5,
+                 "pipelines_per_gpu": len(sh5.engines), "input": "device float32 RGBA [4,1080,1920,4] batches, 8 base pairs cycle",
+                 "algorithmic_bytes_per_frame": int(alg5), "hbm_roofline_frames_per_s_per_gpu": peak * 1e9 / alg5,
+                 "frac_of_hbm_roofline": rate5 / world * alg5 / 1e9 / peak}
+    return out
+
+
+def batched_reference(args, rank, world, local):
+    """The same split on the reference: one engine per rank, a sequential loop over the rank's envs / frames (the reference
+    has no batch API).  Bounded samples: every local C4 env once; up to 16 local C5 frames."""
+    import torch
+
+    from oracle import RefEngine, configs
+    from sapien_b200 import sharding
+
+    out = {}
+    prm = configs.params("C4")
+    a, b = sharding.env_range(args.c4_envs, rank, world)
+    (l, r), = c4_inputs(prm, a, b, 1, torch)
+    ref = RefEngine(prm)
+    stride = prm.rows * prm.cols * 16
+    for i in range(min(8, b - a)):
+        ref.compute_device(l.data_ptr() + i * stride, r.data_ptr() + i * stride, None)
+    torch.cuda.synchronize()
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(b - a):
+        ref.compute_device(l.data_ptr() + i * stride, r.data_ptr() + i * stride, None)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    out["C4"] = {"workload": f"C4: {args.c4_envs} envs x 256x256, 64 disp, split env_range({args.c4_envs}, rank, {world}); sequential loop per rank",
+                 "env_frames_per_s": args.c4_envs / (ms / 1e3), "envs_per_gpu": b - a, "n_gpus": world, "scaling": "strong", "steps": 1, "ms_per_step": ms}
+    ref.close()
+    del l, r
+    torch.cuda.empty_cache()
+    prm = configs.params("C5")
+    f0, f1 = sharding.env_range(args.c5_frames, rank, world)
+    n = min(16, f1 - f0)
+    bl, br = c5_inputs(prm, torch)
+    ref = RefEngine(prm)
+    stride = prm.rows * prm.cols * 16
+    for i in range(2):
+        ref.compute_device(bl.data_ptr() + i * stride, br.data_ptr() + i * stride, None)
+    torch.cuda.synchronize()
+    barrier(world)
+    e0.record()
+    for i in range(n):
+        ref.compute_device(bl.data_ptr() + (i % 8) * stride, br.data_ptr() + (i % 8) * stride, None)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    out["C5"] = {"workload": f"C5: 1920x1080, 256 disp, frames split contiguously over {world} ranks; sequential loop per rank",
+                 "frames_per_s": n * world / (ms / 1e3) if n else 0.0, "sample": f"{n} frames per rank (of {f1 - f0})", "n_gpus": world, "scaling": "strong"}
+    ref.close()
+    return out
+
+
 def run_ours(args, rank, world, local):
     import torch
 
@@ -215,9 +423,11 @@ def run_ours(args, rank, world, local):
     stream = torch.cuda.ExternalStream(eng.cuda_stream, device=torch.device("cuda", local))
     bb = (True, *bbox_t) if bbox_t else (False, 0, 0, 0, 0)
 
+    own = eng.cuda_stream  # stream=own: the inputs are resident and complete, no ordering against a caller stream
+
     def step(i):
         l, r = dev_sets[i % n_sets]
-        eng.compute(l, r, *bb, sync=False)
+        eng.compute(l, r, *bb, stream=own, sync=False)
         if pc:
             eng.get_rgb_point_cloud_cuda(rgba)
 
@@ -250,37 +460,59 @@ def run_ours(args, rank, world, local):
     frames = batch * args.steps * world
     value = frames / (ms / 1e3)
 
-    # ---- e2e: public API, pinned host buffers, H2D + D2H inside the timed region ---------------
+    # ---- e2e: public API, HOST buffers, H2D + D2H inside the timed region -------------------------
+    # (a) extension path: pinned inputs, depth map streamed into a bound pinned buffer;
+    # (b) strict reference signature: plain (pageable) numpy inputs, compute(l, r) + get_ndarray() returning a new array.
     pin_l = [torch.from_numpy(l).pin_memory() for l, _ in host_sets]
     pin_r = [torch.from_numpy(r).pin_memory() for _, r in host_sets]
     out_shape = ((batch,) if batch > 1 else ()) + (prm.rgb_rows, prm.rgb_cols)
     pin_out = torch.empty(out_shape, dtype=torch.float32).pin_memory()
     out_np = pin_out.numpy()
     e2e_steps = max(3, min(args.steps, 30))
+
+    def e2e_loop(fn):
+        for i in range(3):
+            fn(i)
+        barrier(world)
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            fn(i)
+        torch.cuda.synchronize()
+        return max_over_ranks(time.perf_counter() - t0, world)
+
+    def ext_step(i):
+        eng.compute(pin_l[i % n_sets].numpy(), pin_r[i % n_sets].numpy(), *bb)
+        eng.get_ndarray(out=out_np)
+
+    keep = [None]
+
+    def strict_step(i):
+        eng.compute(host_sets[i % n_sets][0], host_sets[i % n_sets][1], *bb)
+        keep[0] = eng.get_ndarray()
+
     eng.bind_output(out_np)  # the depth map streams into the pinned buffer behind the last aggregation pass
-    for i in range(3):
-        eng.compute(pin_l[i % n_sets].numpy(), pin_r[i % n_sets].numpy(), *bb)
-        eng.get_ndarray(out=out_np)
-    barrier(world)
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        eng.compute(pin_l[i % n_sets].numpy(), pin_r[i % n_sets].numpy(), *bb)
-        eng.get_ndarray(out=out_np)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0, world)
-    e2e = {"value": batch * e2e_steps * world / e2e_s, "unit": "frames/s",
-           "h2d_bytes_per_step": int(2 * batch * prm.rows * prm.cols), "d2h_bytes_per_step": int(out_np.nbytes),
-           "api": "DepthSensorEngine.bind_output(pinned) once; per step compute(left_u8, right_u8[, bbox]) + get_ndarray(out=pinned)", "steps": e2e_steps}
+    ext_s = e2e_loop(ext_step)
     eng.bind_output(None)
+    strict_s = e2e_loop(strict_step)
+    h2d, d2h = int(2 * batch * prm.rows * prm.cols), int(out_np.nbytes)
+    e2e = {"value": batch * e2e_steps * world / ext_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "api": "extension path: DepthSensorEngine.bind_output(pinned) once; per step compute(left_u8 pinned, right_u8 pinned[, bbox]) + get_ndarray(out=pinned)",
+           "steps": e2e_steps,
+           "strict": {"value": batch * e2e_steps * world / strict_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                      "api": "reference signature only: compute(left_u8 ndarray, right_u8 ndarray[, bbox]) + get_ndarray() -> new ndarray (pageable inputs, "
+                             "engine-owned pinned staging, one host memcpy into the returned array)"}}
+
+    batched = None
+    del dev_sets
+    if not args.no_batched:
+        del eng
+        torch.cuda.empty_cache()
+        batched = batched_ours(args, rank, world, local)
 
     if rank != 0:
         return
     # ---- roofline of the dominant kernel ---------------------------------------------------------
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    peak, peak_src = hbm_peak()
     s = (prm.rows * prm.cols) if bbox_t is None else bbox_t[2] * bbox_t[3]
     V = 2 * s * prm.max_disp * batch
     kernel_bytes = {"cost": 8 * s * batch + V, "aggr_left": 2 * V, "aggr_down": 2 * V, "aggr_left_down": 4 * V, "aggr_up": 4 * V, "aggr_right_wta": 2 * V + 6 * s * batch}
@@ -288,15 +520,17 @@ def run_ours(args, rank, world, local):
     dom = max((k for k in kernel_bytes if k in st_ms), key=lambda k: st_ms[k], default=None)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic_c1.json")
+    traffic_src = None
     if args.workload == "C1" and batch == 1 and os.path.exists(tpath):  # measured DRAM bytes per launch from the committed ncu capture
-        traffic = json.load(open(tpath))["dram_bytes_per_launch"]
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/traffic_c1.json (" + tj.get("source", "ncu --set full capture") + ")"
     roofline = None
     if dom:
         ach = kernel_bytes[dom] / (st_ms[dom] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": {"cost": "cost_kernel", "aggr_left": "aggr_kernel<MODE 0> (right->left)", "aggr_down": "aggr_kernel<MODE 0> (top->bottom)",
                                                "aggr_left_down": "aggr_kernel<MODE 0> x2 (right->left || top->bottom, two streams)",
                                                "aggr_up": "aggr_kernel<MODE 1> (bottom->top + L1 + L2)", "aggr_right_wta": "aggr_wta_kernel (left->right + blend + WTA)"}[dom],
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": (traffic or {}).get(dom),
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": (traffic or {}).get(dom), "traffic_source": traffic_src,
                     "algorithmic_bytes_per_launch": int(kernel_bytes[dom]), "avg_launch_ms": st_ms[dom], "peak_source": peak_src,
                     "per_kernel_gbs": {k: kernel_bytes[k] / (st_ms[k] * 1e-3) / 1e9 for k in kernel_bytes if k in st_ms}}
     alg = configs.algorithmic_bytes(prm, rgba_input=True, bbox=bbox_t, point_cloud=pc) * batch
@@ -304,24 +538,25 @@ def run_ours(args, rank, world, local):
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u16", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "batch_per_gpu": batch, "input": "device float32 RGBA pairs (reference CUDA input format)",
-                   "l2": f"{n_sets} distinct input sets rotate; per-step intermediate traffic (3 u16 volumes = {3 * V / 1e6:.0f} MB) exceeds the 126 MB L2" if 3 * V > 126e6
-                   else f"{n_sets} distinct input sets rotate; volumes of one batch = {3 * V / 1e6:.0f} MB",
-                   "pipelining": "frames enqueued back to back on the engine's stream; the front-end of frame k+1 (helper stream) overlaps the final pass / post-processing of frame k",
-                   "parallelism": f"env-sharded x{world}, no collective"},
+        "config": shared_config(args, desc, batch, world),
+        "arm": {"impl": "sapien_b200 (this repo)", "volumes_mb": 3 * V / 1e6,
+                "pipelining": "frames enqueued back to back on the engine's stream; the front-end of frame k+1 (helper stream) overlaps the final pass / post-processing of frame k"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches * args.steps,
         "roofline": roofline,
         "frame_roofline": {"algorithmic_bytes_per_step": int(alg), "achieved_gbs": alg / (ms / args.steps * 1e-3) / 1e9 ,
                            "frac_of_peak": alg / (ms / args.steps * 1e-3) / 1e9 / peak},
         "stages_ms": st_ms,
     }
+    if batched is not None:
+        line["batched"] = batched
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(prm, bbox_t, args.cpu_seconds)
     print(json.dumps(line))
 
 
 def run_reference(args, rank, world, local):
-    """The unmodified reference simsense (oracle/_ref) through its own compute()/getMat2d() API."""
+    """The unmodified reference simsense (oracle/_ref) through its own compute()/getMat2d() API.  Nothing of this
+    repo's engine is imported on this arm (the camera presets and the synthetic images are plain Python/numpy)."""
     import torch
 
     from oracle import REF_SO, RefEngine, configs
@@ -335,7 +570,7 @@ def run_reference(args, rank, world, local):
         batch = args.batch
     prm = configs.params(key)
     bbox_t = configs.BBOX_C2 if bbox else None
-    ref = RefEngine(prm)  # the reference has no batch API: a batch is a sequential loop
+    ref = RefEngine(prm)  # the reference has no batch API: a batch is a sequential loop over its environments
     n_sets = 8
     host_sets, dev_sets = make_inputs(prm, 1, n_sets, torch)
     rgba = None
@@ -344,14 +579,13 @@ def run_reference(args, rank, world, local):
 
         rgba = torch.from_numpy(synth.make_rgb(prm.rgb_rows, prm.rgb_cols, 0)).cuda()
     steps = args.steps
-    per_step = min(batch, 8)  # bounded sample of a batched workload
 
     def step(i):
-        for b in range(per_step):
+        for b in range(batch):
             l, r = dev_sets[(i + b) % n_sets]
             ref.compute_device(l.data_ptr(), r.data_ptr(), bbox_t)
             if pc:
-                ref.lib.ref_get_rgb_point_cloud  # host copy is part of the reference getter; skip in the device-timed loop
+                ref.rgb_point_cloud_device(rgba.data_ptr())
 
     for i in range(args.warmup):
         step(i)
@@ -368,31 +602,38 @@ def run_reference(args, rank, world, local):
     barrier(world)
     ms = max_over_ranks(e0.elapsed_time(e1), world)
     clocks = sampler.stop()
-    value = per_step * steps * world / (ms / 1e3)
+    value = batch * steps * world / (ms / 1e3)
     e2e_steps = max(3, min(steps, 20))
     out = None
     for i in range(2):
         ref.compute_host(*host_sets[i % n_sets], bbox_t)
         out = ref.depth()
+    barrier(world)
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         ref.compute_host(*host_sets[i % n_sets], bbox_t)
         out = ref.depth()
     e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+    ref.close()
+    del dev_sets
+    torch.cuda.empty_cache()
+    batched = None if args.no_batched else batched_reference(args, rank, world, local)
     if rank != 0:
         return
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "batch_per_gpu": per_step,
-                   "input": "device float32 RGBA pairs through simsense::DepthSensorEngine::compute(void*, void*, ...)",
-                   "note": "unmodified reference simsense CUDA sources recompiled for sm_100a (oracle/_ref); the reference has no CPU implementation of this path and no batch API (a batch is a sequential loop)"},
+        "config": shared_config(args, desc, batch, world),
+        "arm": {"impl": "unmodified reference simsense CUDA sources recompiled for sm_100a (oracle/_ref), through simsense::DepthSensorEngine::compute(void*, void*, ...)",
+                "note": "the reference has no CPU implementation of this path and no batch API (a batch is a sequential loop)"},
         "clocks": clocks,
         "e2e": {"value": e2e_steps * world / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(2 * prm.rows * prm.cols),
                 "d2h_bytes_per_step": int(out.nbytes), "api": "DepthSensorEngine::compute(Mat2d<u8>, Mat2d<u8>) + getMat2d()", "steps": e2e_steps},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": 0, "kind": "reference",
                          "sample": "reference simsense is CUDA-only: this arm runs its own kernels on the same B200 (0 host compute threads)"},
     }
+    if batched is not None:
+        line["batched"] = batched
     print(json.dumps(line))
 
 

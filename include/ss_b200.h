@@ -87,13 +87,34 @@ typedef struct {
 int ss_compute_host_u8(ss_engine *e, const uint8_t *left, const uint8_t *right,
                        const ss_bbox *bbox);
 /* E:60-61 / C:332-345: device float32 RGBA [batch][rows][cols][4]; the IR value is the R channel
- * (C:45-62).  Enqueued on `stream` (0 = the engine's own stream) and NOT synchronised: the
- * result pointers are valid for work ordered after this call on the same stream. */
+ * (C:45-62).  Ordered after everything already enqueued on `stream` (a cudaStream_t; the special
+ * handles cudaStreamLegacy (0x1) and cudaStreamPerThread (0x2) are accepted) and NOT synchronised:
+ * `stream` is made to wait for the result, so the result pointers are valid for work enqueued on it
+ * after this call.  stream = 0 (or the engine's own stream, ss_get_stream) means "the inputs are
+ * already complete": no ordering is established, the work simply follows the engine's previous
+ * frame.  The reference orders by a cudaDeviceSynchronize at the start of the frame (C:547); a
+ * caller that wants that behaviour passes cudaStreamLegacy and calls ss_synchronize afterwards
+ * (this is what the Python binding does by default).  The colour image of
+ * ss_get_rgb_point_cloud_* is ordered after the legacy default stream. */
 int ss_compute_device_rgba_f32(ss_engine *e, const void *left, const void *right,
                                const ss_bbox *bbox, void *stream);
+/* The same for PITCHED views: environment n starts env_pitch_bytes * n after the base pointer, image row y
+ * row_pitch_bytes * y after that; a pixel is always 4 consecutive floats.  This is how a window of
+ * sapien's BatchedCamera buffer ([N,H,W,4] float32 CudaArrayHandle with byte strides,
+ * src/sapien_renderer/batched_render_system.cpp:76-84) or any sliced tensor is consumed in place; order
+ * the frame after the renderer with `stream` = the stream given to BatchedCamera::setCudaStream
+ * (include/sapien/sapien_renderer/batched_render_system.h:35, the stream its external-semaphore wait
+ * is enqueued on, batched_render_system.cpp:141-145). */
+int ss_compute_device_rgba_f32_pitched(ss_engine *e, const void *left, const void *right,
+                                       size_t env_pitch_bytes, size_t row_pitch_bytes,
+                                       const ss_bbox *bbox, void *stream);
 /* Extension: device uint8 [batch][rows][cols] pairs, same ordering rule. */
 int ss_compute_device_u8(ss_engine *e, const void *left, const void *right, const ss_bbox *bbox,
                          void *stream);
+/* Extension: orders the NEXT compute of this engine after everything already enqueued on `stream`
+ * (a producer stream other than the one passed to the compute call, e.g. the `stream` entry of a
+ * __cuda_array_interface__ v3 input).  No host synchronisation. */
+int ss_wait_stream(ss_engine *e, void *stream);
 /* Waits for the last enqueued compute. */
 int ss_synchronize(ss_engine *e);
 

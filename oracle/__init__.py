@@ -20,6 +20,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libsimsense_ref.so")
+REF_TIMED_SO = os.path.join(HERE, "_ref", "libsimsense_ref_timed.so")  # same sources, -DPRINT_RUNTIME
 
 
 def build(ref: bool = True) -> None:
@@ -197,7 +198,7 @@ class Oracle:
         return pc
 
 
-_REF_STAGES = {"rawim0": np.uint8, "rawim1": np.uint8, "recim0": np.uint8, "recim1": np.uint8, "bboxim0": np.uint8,
+_REF_STAGES = {"rawim0": np.uint8, "rawim1": np.uint8, "noisyim0": np.uint8, "noisyim1": np.uint8, "recim0": np.uint8, "recim1": np.uint8, "bboxim0": np.uint8,
                "bboxim1": np.uint8, "census0": np.uint32, "census1": np.uint32, "rawcost": np.uint16,
                "hsum": np.uint16, "cost": np.uint16, "L0": np.uint16, "L1": np.uint16, "L2": np.uint16,
                "LAll": np.uint16, "leftDisp": np.float32, "rightDisp": np.uint16, "filteredDisp": np.float32,
@@ -207,10 +208,10 @@ _REF_STAGES = {"rawim0": np.uint8, "rawim1": np.uint8, "recim0": np.uint8, "reci
 class RefEngine:
     """The unmodified reference simsense::DepthSensorEngine (registration ctor) on the current GPU."""
 
-    def __init__(self, prm: Params):
-        if not os.path.exists(REF_SO):
-            raise FileNotFoundError(f"{REF_SO} missing: run `make -C oracle ref` where /root/reference exists")
-        lib = C.CDLL(REF_SO)
+    def __init__(self, prm: Params, so: str = REF_SO):
+        if not os.path.exists(so):
+            raise FileNotFoundError(f"{so} missing: run `make -C oracle ref` where /root/reference exists")
+        lib = C.CDLL(so)
         self.lib = lib
         lib.ref_create.restype = C.c_void_p
         lib.ref_create.argtypes = ([C.c_uint32] * 4 + [C.c_float] * 4 + [C.c_uint64] + [C.c_float] * 4 + [C.c_int] * 3 +
@@ -228,6 +229,8 @@ class RefEngine:
         lib.ref_get_point_cloud.argtypes = [C.c_void_p, C.c_void_p]
         lib.ref_get_rgb_point_cloud.restype = C.c_long
         lib.ref_get_rgb_point_cloud.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ref_get_rgb_point_cloud_device.restype = C.c_void_p
+        lib.ref_get_rgb_point_cloud_device.argtypes = [C.c_void_p, C.c_void_p]
         lib.ref_get_stage.restype = C.c_long
         lib.ref_get_stage.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]
         for n in ("ref_set_penalties", "ref_set_census_window_size", "ref_set_matching_block_size"):
@@ -293,6 +296,12 @@ class RefEngine:
             raise RuntimeError(self.lib.ref_last_error().decode())
         return out
 
+    def rgb_point_cloud_device(self, rgba_ptr: int) -> int:
+        p = self.lib.ref_get_rgb_point_cloud_device(self.h, rgba_ptr)
+        if not p:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+        return p
+
     def stage(self, name: str) -> np.ndarray:
         dt = np.dtype(_REF_STAGES[name])
         D = self.prm.max_disp
@@ -305,7 +314,7 @@ class RefEngine:
         a = buf[:n].view(dt)
         if name in ("rawcost", "hsum", "cost", "L0", "L1", "L2", "LAll"):
             return a.reshape(*self.mshape, D)
-        if name in ("rawim0", "rawim1", "recim0", "recim1", "bboxDisp", "depth"):
+        if name in ("rawim0", "rawim1", "noisyim0", "noisyim1", "recim0", "recim1", "bboxDisp", "depth"):
             return a.reshape(self.prm.rows, self.prm.cols)
         if name == "rgbDepth":
             return a.reshape(self.prm.rgb_rows, self.prm.rgb_cols)

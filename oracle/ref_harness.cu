@@ -29,6 +29,8 @@ struct RefEngine : public simsense::DepthSensorEngine {
     const size_t fsz = (size_t)fullRows * fullCols;
     if (n == "rawim0") { *p = d_rawim0; *bytes = fsz; return true; }
     if (n == "rawim1") { *p = d_rawim1; *bytes = fsz; return true; }
+    if (n == "noisyim0" && speckleShape > 0) { *p = d_noisyim0; *bytes = fsz; return true; }
+    if (n == "noisyim1" && speckleShape > 0) { *p = d_noisyim1; *bytes = fsz; return true; }
     if (n == "recim0" && !rectified) { *p = d_recim0; *bytes = fsz; return true; }
     if (n == "recim1" && !rectified) { *p = d_recim1; *bytes = fsz; return true; }
     if (n == "bboxim0") { *p = d_bboxim0; *bytes = sz; return true; }
@@ -160,6 +162,17 @@ long ref_get_rgb_point_cloud(void *h, void *rgbaDevice, float *out) {
   } catch (std::exception &ex) {
     g_err = ex.what();
     return -1;
+  }
+}
+
+// getRgbPointCloudCudaPtr() (core.cu:436-455): the device-side getter, no host copy.  Returns the pointer or null.
+void *ref_get_rgb_point_cloud_device(void *h, void *rgbaDevice) {
+  auto *e = static_cast<RefEngine *>(h);
+  try {
+    return e->getRgbPointCloudCudaPtr(rgbaDevice);
+  } catch (std::exception &ex) {
+    g_err = ex.what();
+    return nullptr;
   }
 }
 

@@ -34,7 +34,6 @@
 #include "kernels.h"
 
 #include <cuda.h> // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
-#include <cstdlib>
 
 namespace ssb {
 
@@ -696,10 +695,9 @@ static cudaError_t launch_one(const AggrArgs &a_in, cudaStream_t st) {
     if (bsmem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem)) != cudaSuccess) return e;
     k<<<(unsigned)((npaths + ppb - 1) / ppb), (unsigned)(64 * ppb), bsmem, st>>>(a);
   } else {
-    static const bool no_tma = getenv("SSB_AGGR_NO_TMA") != nullptr;
     // (rows of D*2 bytes that are not whole 128-byte lines -- D = 96 -- measured slower as tensor boxes
     // than as bulk pieces: C3 top->bottom 1.61 ms vs 1.74 ms)
-    if (a.vertical && !no_tma && a.D <= 256 && a.D * 2 % 128 == 0 && (long)a.N * a.rows < 0x7fffffffL) {
+    if (a.vertical && a.D <= 256 && a.D * 2 % 128 == 0 && (long)a.N * a.rows < 0x7fffffffL) {
       bool ok = make_volume_map(&a.tm[0], a.C, a.N, a.rows, a.cols, a.D, K);
       if (MODE == 1) ok = ok && make_volume_map(&a.tm[1], a.aux0, a.N, a.rows, a.cols, a.D, K) &&
                             make_volume_map(&a.tm[2], a.aux1, a.N, a.rows, a.cols, a.D, K);
@@ -752,13 +750,7 @@ static cudaError_t common_args(AggrArgs &a, const AggrBuffers &b, int N, int row
   a.P1P1 = (uint32_t)P1 * 0x10001u;
   a.P2P2 = (uint32_t)P2 * 0x10001u;
   a.uniq = uniq;
-  static int nsm = 0;
-  if (nsm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) nsm = 148;
-  }
-  a.nsm = nsm;
+  a.nsm = sm_count();
   return cudaSuccess;
 }
 
@@ -772,30 +764,21 @@ cudaError_t launch_aggr_passes(const AggrBuffers &b, int N, int rows, int cols, 
   // right->left and top->bottom are independent.  Alone, each leaves HBM bandwidth unused (the
   // horizontal pass is bound by its 1280-step serial chain, 92 us + 92 us back to back); forked onto
   // two streams -- with the blocks of BOTH kernels resident together -- the pair takes 164 us.
-  // SSB_AGGR_FORK=0 runs them back to back.
-  static const int fork = getenv("SSB_AGGR_FORK") ? atoi(getenv("SSB_AGGR_FORK")) : 2;
   AggrArgs h = a;
   h.vertical = 0; h.reverse = 1; h.out = b.L1;
   AggrArgs v = a;
   v.vertical = 1; v.reverse = 0; v.out = b.L2;
-  if (fork) {
-    if ((err = cudaEventRecord(ev[0], stream)) != cudaSuccess) return err;
-    if ((err = cudaStreamWaitEvent(s_aux, ev[0], 0)) != cudaSuccess) return err;
-    // ring depths measured on C1 (horizontal/vertical slots -> pair + following pass, us): 2/2 166+148, 3/2 166+140,
-    // 4/2 164+140, 2/3 172+148, 3/3 175+150, 4/3 177+146.  The latency-bound horizontal pass wants the deep
-    // ring; the vertical one (tensor copies) finishes last, which leaves its bottom rows in L2 for the
-    // bottom->top pass that starts there.
-    if ((err = dispatch<0, 2>(v, s_aux)) != cudaSuccess) return err;
-    if ((err = dispatch<0, 4>(h, stream)) != cudaSuccess) return err;
-    if ((err = cudaEventRecord(ev[1], s_aux)) != cudaSuccess) return err;
-    if ((err = cudaStreamWaitEvent(stream, ev[1], 0)) != cudaSuccess) return err;
-    mark("aggr_left_down"); // one interval: the two kernels run concurrently
-  } else {
-    if ((err = dispatch<0>(h, stream)) != cudaSuccess) return err;
-    mark("aggr_left");
-    if ((err = dispatch<0>(v, stream)) != cudaSuccess) return err;
-    mark("aggr_down");
-  }
+  if ((err = cudaEventRecord(ev[0], stream)) != cudaSuccess) return err;
+  if ((err = cudaStreamWaitEvent(s_aux, ev[0], 0)) != cudaSuccess) return err;
+  // ring depths measured on C1 (horizontal/vertical slots -> pair + following pass, us): 2/2 166+148, 3/2 166+140,
+  // 4/2 164+140, 2/3 172+148, 3/3 175+150, 4/3 177+146.  The latency-bound horizontal pass wants the deep
+  // ring; the vertical one (tensor copies) finishes last, which leaves its bottom rows in L2 for the
+  // bottom->top pass that starts there.
+  if ((err = dispatch<0, 2>(v, s_aux)) != cudaSuccess) return err;
+  if ((err = dispatch<0, 4>(h, stream)) != cudaSuccess) return err;
+  if ((err = cudaEventRecord(ev[1], s_aux)) != cudaSuccess) return err;
+  if ((err = cudaStreamWaitEvent(stream, ev[1], 0)) != cudaSuccess) return err;
+  mark("aggr_left_down"); // one interval: the two kernels run concurrently
   // bottom->top, accumulating L1+L2+L3
   AggrArgs u = a;
   u.vertical = 1; u.reverse = 1; u.aux0 = b.L1; u.aux1 = b.L2; u.out = b.S3; u.dbg0 = b.dbgL3;
@@ -819,19 +802,8 @@ cudaError_t launch_aggr_final(const AggrBuffers &b, int N, int rows, int cols, i
     w.seg_end[i] = seg_end[i];
   }
   // more rows than one wave of 5-row blocks can hold: throughput regime (see launch_one)
-  static const bool no_batched = getenv("SSB_FINAL_NO_BATCHED") != nullptr;
-  if (!no_batched && (long)N * rows > 5L * w.nsm) return dispatch<2, 2>(w, stream);
+  if ((long)N * rows > 5L * w.nsm) return dispatch<2, 2>(w, stream);
   return dispatch<2>(w, stream);
-}
-
-cudaError_t launch_aggr_wta(const AggrBuffers &b, int N, int rows, int cols, int D, int P1, int P2,
-                            int uniq, cudaStream_t stream, cudaStream_t s_aux, cudaEvent_t *ev,
-                            const AggrMarks *marks) {
-  cudaError_t err = launch_aggr_passes(b, N, rows, cols, D, P1, P2, uniq, stream, s_aux, ev, marks);
-  if (err != cudaSuccess) return err;
-  err = launch_aggr_final(b, N, rows, cols, D, P1, P2, uniq, stream, nullptr, 0, nullptr);
-  if (marks) marks->mark(marks->ctx, "aggr_right_wta");
-  return err;
 }
 
 } // namespace ssb

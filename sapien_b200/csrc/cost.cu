@@ -284,8 +284,6 @@ __global__ void cost_generic_kernel(const uint32_t *__restrict__ cL, const uint3
   C[idx] = (uint16_t)acc;
 }
 
-static int g_sm_count = 0;
-
 template <int BW, int BH, int TX, int NS, int TD, bool PACK8, int DT = 0>
 static cudaError_t launch_cfg(const uint32_t *cL, const uint32_t *cR, uint16_t *C, int N, int rows,
                               int cols, int D, cudaStream_t st) {
@@ -294,12 +292,6 @@ static cudaError_t launch_cfg(const uint32_t *cL, const uint32_t *cR, uint16_t *
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
-  if (g_sm_count == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
-  }
   int per_sm = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, TD * NS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   const int nchunks = (D + 2 * TD - 1) / (2 * TD);
@@ -307,7 +299,7 @@ static cudaError_t launch_cfg(const uint32_t *cL, const uint32_t *cR, uint16_t *
   // Row bands: as many as fit in ONE resident wave (a second, partial wave would double the
   // kernel time), at least 24 rows each so that the BH-1 warm-up rows stay a small overhead.
   // Batches that exceed one wave anyway use ~64-row bands.
-  const long capacity = (long)g_sm_count * per_sm;
+  const long capacity = (long)sm_count() * per_sm;
   long bands = capacity / (xb * N);
   const long max_bands = (rows + 23) / 24;
   if (bands > max_bands) bands = max_bands;

@@ -17,6 +17,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h> // header-only; ranges cost nothing unless a profiler is attached
+
 using namespace ssb;
 
 namespace {
@@ -34,6 +36,13 @@ int fail(int code, const std::string &msg) {
     if (_e != cudaSuccess)                                                                        \
       return fail(SS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));               \
   } while (0)
+
+// NVTX range around the enqueue of one stage (the reference brackets its host code the same way,
+// include/sapien/profiler.h:33-38).  Device time per stage: ss_set_profiling / ss_get_stage_times.
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct DeviceGuard {
   int prev = -1;
@@ -75,13 +84,18 @@ struct ss_engine {
   cudaStream_t stream = nullptr, aux = nullptr, cpy = nullptr;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  cudaEvent_t ev_dep = nullptr; // ss_wait_stream: extra producer stream(s) the next compute is ordered after
+  bool dep_pending = false;
   // banded output (ss_bind_output_host): the final SGM pass runs in column segments and the depth map
   // streams to the bound host buffer band by band while the remaining segments compute
   static constexpr int MAXSEG = 6;
   cudaEvent_t ev_seg[MAXSEG] = {}, ev_band[MAXSEG] = {}, ev_copied = nullptr;
-  float *host_out = nullptr;
+  float *host_out = nullptr;    // caller-bound output (ss_bind_output_host)
   size_t host_cap = 0;
-  bool streamed = false;        // the last compute delivered its depth map into host_out
+  float *staging = nullptr;     // engine-owned pinned output of host-input frames when nothing is bound (the
+                                // reference stages every read-back through an engine-owned host buffer, core.cu:347-362)
+  float *stream_dst = nullptr;  // where the last compute streamed its depth map (host_out, staging or null)
+  bool streamed = false;        // the last compute delivered its depth map into stream_dst
   std::vector<int> rgb_sufmin;  // [cols+1] smallest RGB column any matched column >= x can splat into (empty: banding off)
   uint32_t *progress = nullptr; // [MAXSEG] rows finished per column segment of the final pass
 
@@ -160,6 +174,7 @@ int create_impl(ss_engine *e, const float *mapLx, const float *mapLy, const floa
   CK(cudaEventCreateWithFlags(&e->ev_front, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&e->ev_dep, cudaEventDisableTiming));
   const size_t fsz = e->fsz(), N = (size_t)c.batch;
   int r;
   if (!c.rectified) {
@@ -181,6 +196,11 @@ int create_impl(ss_engine *e, const float *mapLx, const float *mapLy, const floa
   if (c.registration) {
     const double zmin = (double)c.focal_len * c.baseline_len / (double)c.max_disp;
     bool ok = zmin > 0;
+    if (c.b3 > 0) { // invalid disparities give z = 0 and splat zRgb = b3 at (b1/b3, b2/b3) (camera.cu:187-195):
+      // if that pixel is inside the RGB image any band may write it, so no RGB column is ever final early
+      const double u0 = std::round((double)c.b1 / c.b3), v0 = std::round((double)c.b2 / c.b3);
+      if (u0 >= 0 && u0 < (double)c.rgb_cols && v0 >= 0 && v0 < (double)c.rgb_rows) ok = false;
+    }
     std::vector<int> colmin(c.cols, INT32_MAX);
     for (uint32_t y = 0; ok && y < c.rows; ++y)
       for (uint32_t x = 0; x < c.cols; ++x) {
@@ -198,7 +218,10 @@ int create_impl(ss_engine *e, const float *mapLx, const float *mapLy, const floa
   }
   // cost volumes: C, L1, L2 (S3 aliases L2) -- or 7 separate ones with keep_stages
   const size_t vol = fsz * (size_t)c.max_disp * sizeof(uint16_t);
-  const int nvol = c.keep_stages ? 7 : 3;
+  // (configurations outside the packed-u16 regime aggregate through generic.cu, which needs three more volumes)
+  const bool fast0 = aggr_fast_supported(c.max_disp, census_bits(c.census_width, c.census_height) * c.bf_width * c.bf_height,
+                                         c.p1 * c.bf_width * c.bf_height, c.p2 * c.bf_width * c.bf_height);
+  const int nvol = c.keep_stages ? 7 : (fast0 ? 3 : 6);
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   const size_t small = N * (fsz * 40 + e->rsz() * 48) + (64u << 20);
@@ -241,9 +264,12 @@ enum InputKind { IN_U8, IN_RGBA };
 
 // host_left / host_right: when non-null (host-u8 path, one wave, 7x7 census) the uploads happen here,
 // the right image on the helper stream, so that the left image's front-end overlaps the second upload
+// inputs_on_main: left/right are engine-owned buffers whose uploads were enqueued on the main stream
 int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *right,
                  const ss_bbox *bbox, cudaStream_t user, const uint8_t *host_left = nullptr,
-                 const uint8_t *host_right = nullptr) {
+                 const uint8_t *host_right = nullptr, bool inputs_on_main = false,
+                 size_t env_pitch = 0, size_t row_pitch = 0) { // pitches in source elements, 0 = packed
+  NvtxRange nvtx_frame("ss_b200::compute");
   const ss_config &c = e->cfg;
   if (!left || !right) return fail(SS_ERR_INVALID, "null input image");
   int bx = 0, by = 0, rows = (int)c.rows, cols = (int)c.cols, use_bbox = 0;
@@ -262,6 +288,10 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
     CK(cudaEventRecord(e->ev_in, user));
     CK(cudaStreamWaitEvent(st, e->ev_in, 0));
   }
+  if (e->dep_pending) { // (the main stream already waits on it, see ss_wait_stream; the front-end may run on the helper stream)
+    CK(cudaStreamWaitEvent(e->aux, e->ev_dep, 0));
+    e->dep_pending = false;
+  }
   if (e->pev.size() > 4096) { // profiling left on without anybody reading: drop the backlog
     for (auto ev : e->pev) cudaEventDestroy(ev);
     e->pev.clear(); e->pnames.clear();
@@ -279,7 +309,10 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
   // Banded output plan (see ss_bind_output_host): up to 4 progress points of the final pass -> up to 5 bands
   int nseg = 0, seg_end[ss_engine::MAXSEG];
   bool banded = false;
-  if (e->host_out && fast && !use_bbox && !c.keep_stages && c.batch <= e->wave &&
+  // Host-input frames have a host consumer: without a bound buffer they stream into the engine's own pinned
+  // staging buffer and ss_get_depth_host copies from there (a pageable 8.3 MB cudaMemcpy costs ~2 ms at C1).
+  float *band_dst = e->host_out ? e->host_out : ((host_left || inputs_on_main) ? e->staging : nullptr);
+  if (band_dst && fast && !use_bbox && !c.keep_stages && c.batch <= e->wave &&
       (!c.registration || !e->rgb_sufmin.empty())) {
     // progress points (3, 4 and 5 points measured within 1 % of each other on C1: the copy engine is the bound --
     // ~155 us for the map, starting when the first band is final -- not the band count)
@@ -296,12 +329,15 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
   for (int w0 = 0; w0 < c.batch; w0 += e->wave) {
     const int wn = std::min(e->wave, c.batch - w0);
     FrontParams fp{};
+    const size_t epx = kind == IN_U8 ? 1 : 4; // source elements per texel
+    fp.src_env = env_pitch ? env_pitch : fsz * epx;
+    fp.src_row = (uint32_t)(row_pitch ? row_pitch : (size_t)c.cols * epx);
     if (kind == IN_U8) {
-      fp.left_u8 = static_cast<const uint8_t *>(left) + (size_t)w0 * fsz;
-      fp.right_u8 = static_cast<const uint8_t *>(right) + (size_t)w0 * fsz;
+      fp.left_u8 = static_cast<const uint8_t *>(left) + (size_t)w0 * fp.src_env;
+      fp.right_u8 = static_cast<const uint8_t *>(right) + (size_t)w0 * fp.src_env;
     } else {
-      fp.left_rgba = static_cast<const float *>(left) + (size_t)w0 * fsz * 4;
-      fp.right_rgba = static_cast<const float *>(right) + (size_t)w0 * fsz * 4;
+      fp.left_rgba = static_cast<const float *>(left) + (size_t)w0 * fp.src_env;
+      fp.right_rgba = static_cast<const float *>(right) + (size_t)w0 * fp.src_env;
     }
     fp.mapLx = e->mapLx; fp.mapLy = e->mapLy; fp.mapRx = e->mapRx; fp.mapRy = e->mapRy;
     fp.frows = (int)c.rows; fp.fcols = (int)c.cols; fp.bx = bx; fp.by = by;
@@ -315,6 +351,8 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
       fp.canvas = e->canvas; fp.canvas_n = (size_t)c.batch * e->rsz(); fp.canvas_fill = c.max_depth;
     }
     fp.only_image = -1;
+    {
+    NvtxRange nvtx_front("front");
     if (host_left) {
       const size_t bytes = (size_t)c.batch * fsz;
       CK(cudaEventRecord(e->ev[0], st)); // the helper stream starts behind whatever precedes this frame
@@ -337,6 +375,10 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
       // (138 -> 166 us); after that pass it slows the final one (104 -> 123 us).  It fills the OTHER splat
       // canvas (the previous frame's dilation may still be reading its own).
       if (user && user != st) CK(cudaStreamWaitEvent(e->aux, e->ev_in, 0));
+      if (inputs_on_main) { // the uploads into raw0/raw1 sit on the main stream: the helper stream must see them
+        CK(cudaEventRecord(e->ev[0], st));
+        CK(cudaStreamWaitEvent(e->aux, e->ev[0], 0));
+      }
       CK(cudaStreamWaitEvent(e->aux, e->ev_cost, 0)); // (first frame: never recorded, no-op)
       CK(launch_front(fp, e->aux));
       CK(cudaEventRecord(e->ev_front, e->aux));
@@ -344,10 +386,15 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
     } else {
       CK(launch_front(fp, st));
     }
+    }
     e->mark("front");
-    CK(launch_cost(fp.census0, fp.census1, e->C, wn, rows, cols, D, c.bf_width, c.bf_height,
-                   census_bits(c.census_width, c.census_height), st));
+    {
+      NvtxRange nvtx_cost("cost");
+      CK(launch_cost(fp.census0, fp.census1, e->C, wn, rows, cols, D, c.bf_width, c.bf_height,
+                     census_bits(c.census_width, c.census_height), st));
+    }
     e->mark("cost");
+    NvtxRange nvtx_aggr("aggregation+wta");
     AggrBuffers ab{};
     ab.C = e->C; ab.L1 = e->L1; ab.L2 = e->L2; ab.S3 = e->S3;
     ab.dbgL0 = e->dbgL0; ab.dbgL3 = e->dbgL3; ab.dbgLAll = e->dbgLAll;
@@ -373,6 +420,7 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
     }
     if (!fast) e->mark("aggr_wta_generic");
   }
+  NvtxRange nvtx_post("post");
   PostParams pp{};
   pp.N = c.batch; pp.rows = rows; pp.cols = cols; pp.frows = (int)c.rows; pp.fcols = (int)c.cols;
   pp.bx = bx; pp.by = by; pp.bbox = use_bbox; pp.lr_max_diff = c.lr_max_diff; pp.mf_size = c.mf_size;
@@ -388,6 +436,7 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
   pp.canvas = e->canvas; pp.out = e->out;
   pp.canvas_prefilled = 1;
   e->streamed = false;
+  e->stream_dst = nullptr;
   if (banded) {
     // final pass in column segments; behind each segment: post-processing of the columns whose
     // disparities are final (helper stream) and the copy of the finished output columns to the bound
@@ -427,7 +476,7 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
       CK(cudaEventRecord(e->ev_band[s], e->aux));
       if (ub > ua) {
         CK(cudaStreamWaitEvent(e->cpy, e->ev_band[s], 0));
-        CK(cudaMemcpy2DAsync(e->host_out + ua, pitch, e->out + ua, pitch, (size_t)(ub - ua) * sizeof(float),
+        CK(cudaMemcpy2DAsync(band_dst + ua, pitch, e->out + ua, pitch, (size_t)(ub - ua) * sizeof(float),
                              (size_t)c.batch * orows, cudaMemcpyDeviceToHost, e->cpy));
       }
       xa = xb; ua = ub;
@@ -437,6 +486,7 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
     CK(cudaStreamWaitEvent(st, e->ev_band[nseg], 0));
     CK(cudaStreamWaitEvent(st, e->ev_copied, 0));
     e->streamed = true;
+    e->stream_dst = band_dst;
   } else {
     int pl = 0;
     CK(launch_post(pp, st, &pl));
@@ -498,6 +548,7 @@ int ss_destroy(ss_engine *e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->aux) cudaStreamSynchronize(e->aux);
   for (void *p : e->allocs) cudaFree(p);
+  if (e->staging) cudaFreeHost(e->staging);
   for (auto ev : e->pev) cudaEventDestroy(ev);
   for (auto ev : e->ev) if (ev) cudaEventDestroy(ev);
   for (auto ev : e->ev_seg) if (ev) cudaEventDestroy(ev);
@@ -508,6 +559,7 @@ int ss_destroy(ss_engine *e) {
   if (e->cpy) { cudaStreamSynchronize(e->cpy); cudaStreamDestroy(e->cpy); }
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_out) cudaEventDestroy(e->ev_out);
+  if (e->ev_dep) cudaEventDestroy(e->ev_dep);
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->aux) cudaStreamDestroy(e->aux);
   delete e;
@@ -519,11 +571,16 @@ int ss_compute_host_u8(ss_engine *e, const uint8_t *left, const uint8_t *right, 
   DeviceGuard g(e->device);
   const size_t bytes = (size_t)e->cfg.batch * e->fsz();
   const bool split = e->cfg.census_width == 7 && e->cfg.census_height == 7 && e->cfg.batch <= e->wave;
+  if (!e->host_out && !e->staging) { // first host-input frame without a bound output: allocate the pinned staging buffer
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, (size_t)e->cfg.batch * e->rsz() * sizeof(float), cudaHostAllocDefault) == cudaSuccess) e->staging = static_cast<float *>(p);
+    else cudaGetLastError(); // (no pinned memory to spare: the read-back falls back to a direct copy)
+  }
   if (!split) {
     CK(cudaMemcpyAsync(e->raw0, left, bytes, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(e->raw1, right, bytes, cudaMemcpyHostToDevice, e->stream));
   }
-  int r = compute_impl(e, IN_U8, e->raw0, e->raw1, bbox, nullptr, split ? left : nullptr, split ? right : nullptr);
+  int r = compute_impl(e, IN_U8, e->raw0, e->raw1, bbox, nullptr, split ? left : nullptr, split ? right : nullptr, !split);
   if (r) return r;
   CK(cudaStreamSynchronize(e->stream));
   return SS_OK;
@@ -535,10 +592,38 @@ int ss_compute_device_rgba_f32(ss_engine *e, const void *left, const void *right
   return compute_impl(e, IN_RGBA, left, right, bbox, static_cast<cudaStream_t>(stream));
 }
 
+int ss_compute_device_rgba_f32_pitched(ss_engine *e, const void *left, const void *right, size_t env_pitch_bytes,
+                                       size_t row_pitch_bytes, const ss_bbox *bbox, void *stream) {
+  if (!e) return fail(SS_ERR_INVALID, "null engine");
+  const size_t row_min = (size_t)e->cfg.cols * 16;
+  if (row_pitch_bytes < row_min || row_pitch_bytes % 4 || row_pitch_bytes / 4 > 0xffffffffull ||
+      (e->cfg.rows - 1) * (row_pitch_bytes / 4) + (size_t)e->cfg.cols * 4 > 0xffffffffull)
+    return fail(SS_ERR_INVALID, "row pitch must be a multiple of 4 bytes, at least cols*16, and one image must span < 16 GiB");
+  if (e->cfg.batch > 1 && (env_pitch_bytes % 4 || env_pitch_bytes < (e->cfg.rows - 1) * row_pitch_bytes + row_min))
+    return fail(SS_ERR_INVALID, "environment pitch must be a multiple of 4 bytes and hold one image");
+  if ((reinterpret_cast<uintptr_t>(left) | reinterpret_cast<uintptr_t>(right)) % 4)
+    return fail(SS_ERR_INVALID, "float32 inputs must be 4-byte aligned");
+  DeviceGuard g(e->device);
+  return compute_impl(e, IN_RGBA, left, right, bbox, static_cast<cudaStream_t>(stream), nullptr, nullptr, false,
+                      env_pitch_bytes / 4, row_pitch_bytes / 4);
+}
+
 int ss_compute_device_u8(ss_engine *e, const void *left, const void *right, const ss_bbox *bbox, void *stream) {
   if (!e) return fail(SS_ERR_INVALID, "null engine");
   DeviceGuard g(e->device);
   return compute_impl(e, IN_U8, left, right, bbox, static_cast<cudaStream_t>(stream));
+}
+
+int ss_wait_stream(ss_engine *e, void *stream) {
+  if (!e) return fail(SS_ERR_INVALID, "null engine");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!s || s == e->stream) return SS_OK;
+  DeviceGuard g(e->device);
+  if (e->dep_pending) CK(cudaStreamWaitEvent(e->aux, e->ev_dep, 0)); // a second producer stream: flush the first
+  CK(cudaEventRecord(e->ev_dep, s));
+  CK(cudaStreamWaitEvent(e->stream, e->ev_dep, 0));
+  e->dep_pending = true;
+  return SS_OK;
 }
 
 int ss_synchronize(ss_engine *e) {
@@ -581,8 +666,15 @@ int ss_get_depth_host(ss_engine *e, float *out, size_t cap) {
   if (!e) return fail(SS_ERR_INVALID, "null engine");
   if (!e->computed) return fail(SS_ERR_NOT_COMPUTED, "No computed data stored");
   DeviceGuard g(e->device);
-  if (e->streamed && out == e->host_out) { // already delivered band by band during compute
+  const size_t bytes = (size_t)e->cfg.batch * e->rsz() * sizeof(float);
+  if (e->streamed && out && out == e->stream_dst) { // already delivered band by band during compute
     CK(cudaStreamSynchronize(e->stream));
+    return SS_OK;
+  }
+  if (e->streamed && out && e->stream_dst == e->staging && e->staging) { // delivered into the pinned staging buffer
+    if (cap < bytes) return fail(SS_ERR_INVALID, "output buffer too small");
+    CK(cudaStreamSynchronize(e->stream));
+    std::memcpy(out, e->staging, bytes);
     return SS_OK;
   }
   return copy_out(e, e->out, (size_t)e->cfg.batch * e->rsz(), out, cap);
@@ -596,6 +688,7 @@ int ss_bind_output_host(ss_engine *e, float *out, size_t cap) {
   e->host_out = out;
   e->host_cap = out ? cap : 0;
   e->streamed = false;
+  e->stream_dst = nullptr;
   return SS_OK;
 }
 int ss_get_depth_device(ss_engine *e, void **ptr) {
@@ -606,6 +699,10 @@ int ss_get_depth_device(ss_engine *e, void **ptr) {
 }
 static int run_pc(ss_engine *e, const void *rgba) {
   const ss_config &c = e->cfg;
+  if (rgba) { // the colour image may still be in flight on the caller's (default) stream
+    CK(cudaEventRecord(e->ev_in, cudaStreamLegacy));
+    CK(cudaStreamWaitEvent(e->stream, e->ev_in, 0));
+  }
   CK(launch_point_cloud(e->out, static_cast<const float *>(rgba), rgba ? e->rgbpc : e->pc, c.batch,
                         (int)e->out_rows(), (int)e->out_cols(), c.main_fx, c.main_fy, c.main_skew,
                         c.main_cx, c.main_cy, e->stream));

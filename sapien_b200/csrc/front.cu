@@ -77,6 +77,12 @@ __device__ __noinline__ int ir_noise(const FrontParams &p, int v, size_t sp, int
   return min(max((int)r, 0), 255);
 }
 
+// noise stream id of a texel = its PACKED pixel index inside the environment, whatever the source pitch
+template <bool RGBA> __device__ __noinline__ uint32_t noise_pixel(const FrontParams &p, uint32_t off) {
+  const uint32_t yy = off / p.src_row, xx = (off - yy * p.src_row) / (RGBA ? 4u : 1u);
+  return yy * (uint32_t)p.fcols + xx;
+}
+
 struct Src {
   const uint8_t *u8;
   const float *rgba;
@@ -95,15 +101,15 @@ __device__ __forceinline__ int fetch(const FrontParams &p, const Src &s, int n, 
     sy = fminf(fmaxf(sy, 0.0f), (float)(p.frows - 1));
     fx = (int)sx; fy = (int)sy;
   }
-  const size_t sp = ((size_t)n * p.frows + fy) * p.fcols + fx;
+  const size_t so = (size_t)n * p.src_env + (size_t)fy * p.src_row + (RGBA ? 4 : 1) * (size_t)fx; // pitched source
   int v;
   if (RGBA) {
-    const int t = (int)(__ldg(s.rgba + 4 * sp) * 255); // truncation, core.cu:51
+    const int t = (int)(__ldg(s.rgba + so) * 255); // truncation, core.cu:51
     v = min(max(t, 0), 255);
   } else {
-    v = __ldg(s.u8 + sp);
+    v = __ldg(s.u8 + so);
   }
-  if (p.speckle_shape > 0.0f) v = ir_noise(p, v, sp, which);
+  if (p.speckle_shape > 0.0f) v = ir_noise(p, v, ((size_t)n * p.frows + fy) * p.fcols + fx, which);
   return v;
 }
 
@@ -210,7 +216,9 @@ template <int I, int J> struct CensusBits {
 // One block = one tile of ONE image (blockIdx.z = 2 * env + image): twice the blocks and half the
 // dependent load rounds per block of a both-images block (the kernel is bound by the latency of
 // the map -> texel gather, not by bandwidth).
-template <bool RGBA, int MINB>
+// PITCHED: the source rows / environments are not packed (FrontParams::src_row / src_env); the packed
+// instantiation keeps its tighter address arithmetic (the kernel sits at its register cap).
+template <bool RGBA, int MINB, bool PITCHED>
 __global__ void __launch_bounds__(F7_NT, MINB) front7_kernel(const FrontParams p) {
   __shared__ __align__(16) uint32_t win[1][F7_WH][F7_WB / 4];
   const int tid = threadIdx.x;
@@ -238,9 +246,10 @@ __global__ void __launch_bounds__(F7_NT, MINB) front7_kernel(const FrontParams p
   {
     const Src &s = img ? sr : sl;
     uint8_t *bdst = b0;
-    const size_t envoff = (size_t)n * p.frows * p.fcols;
-    const float *srgba = RGBA ? s.rgba + 4 * envoff : nullptr;
-    const uint8_t *su8 = RGBA ? nullptr : s.u8 + envoff;
+    const size_t envoff = (size_t)n * p.frows * p.fcols; // pixel id of the environment's first texel (noise streams)
+    const size_t envsrc = PITCHED ? (size_t)n * p.src_env : (RGBA ? 4 : 1) * envoff;
+    const float *srgba = RGBA ? s.rgba + envsrc : nullptr;
+    const uint8_t *su8 = RGBA ? nullptr : s.u8 + envsrc;
 #pragma unroll
     for (int h = 0; h < NPH; ++h) {
       int fx[HALF], fy[HALF];
@@ -262,7 +271,7 @@ __global__ void __launch_bounds__(F7_NT, MINB) front7_kernel(const FrontParams p
       }
       float tf[HALF];
       uint8_t tb[HALF];
-      uint32_t sp[HALF]; // texel offset inside environment n (one image is < 4 Gi texels)
+      uint32_t sp[HALF]; // packed: texel index inside environment n; PITCHED: element offset (one image is < 4 Gi elements)
 #pragma unroll
       for (int k = 0; k < HALF; ++k) {
         if (s.mapx) { // camera.cu:83-119: always-snapped nearest neighbour
@@ -270,8 +279,9 @@ __global__ void __launch_bounds__(F7_NT, MINB) front7_kernel(const FrontParams p
           const float sy = fminf(fmaxf(roundf(my[k]), 0.0f), (float)(p.frows - 1));
           fx[k] = (int)sx; fy[k] = (int)sy;
         }
-        sp[k] = (uint32_t)fy[k] * (uint32_t)p.fcols + (uint32_t)fx[k];
-        if (RGBA) tf[k] = __ldg(srgba + 4 * (size_t)sp[k]);
+        if (PITCHED) sp[k] = (uint32_t)fy[k] * p.src_row + (RGBA ? 4u : 1u) * (uint32_t)fx[k];
+        else sp[k] = (uint32_t)fy[k] * (uint32_t)p.fcols + (uint32_t)fx[k];
+        if (RGBA) tf[k] = __ldg(srgba + (PITCHED ? (size_t)sp[k] : 4 * (size_t)sp[k]));
         else tb[k] = __ldg(su8 + sp[k]);
       }
 #pragma unroll
@@ -279,7 +289,7 @@ __global__ void __launch_bounds__(F7_NT, MINB) front7_kernel(const FrontParams p
         int v;
         if (RGBA) v = min(max((int)(tf[k] * 255), 0), 255); // truncation, core.cu:51
         else v = tb[k];
-        if (p.speckle_shape > 0.0f) v = ir_noise(p, v, envoff + sp[k], img);
+        if (p.speckle_shape > 0.0f) v = ir_noise(p, v, envoff + (PITCHED ? noise_pixel<RGBA>(p, sp[k]) : sp[k]), img);
         const int e = (h * HALF + k) * F7_NT + tid;
         if (e < NEL) bdst[e] = (uint8_t)(inside[k] ? v : 0);
       }
@@ -333,8 +343,15 @@ cudaError_t launch_front(const FrontParams &p, cudaStream_t st) {
   if (p.N > 32767) return cudaErrorInvalidValue;
   if (p.cw == 7 && p.ch == 7) {
     const dim3 grid((p.cols + F7_TW - 1) / F7_TW, (p.rows + F7_TH - 1) / F7_TH, (p.only_image < 0 ? 2 : 1) * p.N);
-    if (p.left_rgba) front7_kernel<true, 4><<<grid, F7_NT, 0, st>>>(p);
-    else front7_kernel<false, 4><<<grid, F7_NT, 0, st>>>(p);
+    const bool packed = p.left_rgba ? (p.src_row == 4u * (uint32_t)p.fcols && p.src_env == 4 * (size_t)p.frows * p.fcols)
+                                    : (p.src_row == (uint32_t)p.fcols && p.src_env == (size_t)p.frows * p.fcols);
+    if (p.left_rgba) {
+      if (packed) front7_kernel<true, 4, false><<<grid, F7_NT, 0, st>>>(p);
+      else front7_kernel<true, 4, true><<<grid, F7_NT, 0, st>>>(p);
+    } else {
+      if (packed) front7_kernel<false, 4, false><<<grid, F7_NT, 0, st>>>(p);
+      else front7_kernel<false, 4, true><<<grid, F7_NT, 0, st>>>(p);
+    }
     return cudaGetLastError();
   }
   if (p.only_image >= 0) return cudaErrorInvalidValue; // per-image launches: 7x7 census path only

@@ -12,6 +12,10 @@ struct FrontParams {
   // sources: exactly one of src_u8 / src_rgba per image is non-null.  [N][frows][fcols](x4)
   const uint8_t *left_u8, *right_u8;
   const float *left_rgba, *right_rgba;
+  // source pitches in ELEMENTS of the source type (u8 texels / floats): one image row, one environment.
+  // Packed inputs: frows*fcols(*4) and fcols(*4).  A float RGBA pixel is always 4 consecutive floats.
+  size_t src_env;
+  uint32_t src_row;
   const float *mapLx, *mapLy, *mapRx, *mapRy; // null when rectified
   int frows, fcols;                           // full IR size
   int bx, by;                                 // ROI origin (0,0 when no bbox)
@@ -53,17 +57,13 @@ struct AggrBuffers {
   float *dispL;      // [N][rows][cols] WTA left disparity (uniqueness + sub-pixel), -1 invalid
   uint16_t *dispR;   // [N][rows][cols] WTA right disparity
 };
-// Runs the 4 path aggregations + blend + winner-takes-all.  s_aux is a second stream used to
-// overlap the two independent first passes; ev[0..1] are scratch events.
 struct AggrMarks { // optional per-kernel timing marks (engine profiling mode)
   void (*mark)(void *ctx, const char *name);
   void *ctx;
 };
-cudaError_t launch_aggr_wta(const AggrBuffers &b, int N, int rows, int cols, int D, int P1, int P2,
-                            int uniq, cudaStream_t stream, cudaStream_t s_aux, cudaEvent_t *ev,
-                            const AggrMarks *marks = nullptr);
-// The same in two parts: the three plain passes, then the final pass (left->right + blend +
-// winner-takes-all).  With progress counters the final pass reports, per row, when the columns
+// The 4 path aggregations + blend + winner-takes-all in two parts: the three plain passes (s_aux is a
+// second stream that overlaps the two independent first passes; ev[0..1] are scratch events), then the
+// final pass (left->right + blend + winner-takes-all).  With progress counters the final pass reports, per row, when the columns
 // < seg_end[k] (multiples of 32, ascending, < cols) are finished: progress[k] reaches N*rows when
 // every row is that far -- disparities of the columns < seg_end[k] - D are then final (the right
 // disparity of a pixel completes D-1 columns later).  The caller zeroes the counters beforehand.

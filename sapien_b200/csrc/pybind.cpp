@@ -10,6 +10,7 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <algorithm>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -60,6 +61,7 @@ struct CudaArray {
   std::string type;
   int cuda_id = -1;
   void *ptr = nullptr;
+  uintptr_t stream = 0; // producer stream of a __cuda_array_interface__ v3 object (0: none given)
   py::object owner; // keeps the producer alive (the reference does not; harmless extension)
 
   bool contiguous() const {
@@ -92,6 +94,8 @@ CudaArray from_object(py::object obj) {
   int32_t dev = -1;
   if (a.ptr && ss_pointer_device(a.ptr, &dev) != SS_OK) dev = -1;
   a.cuda_id = dev;
+  if (iface.contains("stream") && !iface["stream"].is_none()) // v3: 1 = legacy default, 2 = per-thread default, else a handle
+    a.stream = iface["stream"].cast<uintptr_t>();
   a.owner = obj;
   return a;
 }
@@ -150,17 +154,17 @@ public:
   DepthSensorEngine(uint32_t rows, uint32_t cols, uint32_t rgbRows, uint32_t rgbCols, float focalLen,
                     float baselineLen, float minDepth, float maxDepth, uint64_t noiseSeed,
                     float speckleShape, float speckleScale, float gaussianMu, float gaussianSigma,
-                    bool rectified, int censusWidth, int censusHeight, int maxDisp, int bfWidth,
-                    int bfHeight, int p1, int p2, int uniqRatio, int lrMaxDiff, int mfSize, F32 mapLx,
+                    bool rectified, uint8_t censusWidth, uint8_t censusHeight, uint32_t maxDisp, uint8_t bfWidth,
+                    uint8_t bfHeight, uint8_t p1, uint8_t p2, uint8_t uniqRatio, int lrMaxDiff, uint8_t mfSize, F32 mapLx,
                     F32 mapLy, F32 mapRx, F32 mapRy, F32 a1, F32 a2, F32 a3, float b1, float b2,
                     float b3, bool dilation, float mainFx, float mainFy, float mainSkew, float mainCx,
-                    float mainCy, int device, int batch, bool keepStages) {
+                    float mainCy, int device, int batch, bool keepStages, bool batched) {
     ss_config c{};
     c.rows = rows; c.cols = cols; c.rgb_rows = rgbRows; c.rgb_cols = rgbCols;
     c.focal_len = focalLen; c.baseline_len = baselineLen; c.min_depth = minDepth; c.max_depth = maxDepth;
     c.ir_noise_seed = noiseSeed; c.speckle_shape = speckleShape; c.speckle_scale = speckleScale;
     c.gaussian_mu = gaussianMu; c.gaussian_sigma = gaussianSigma; c.rectified = rectified;
-    c.census_width = censusWidth; c.census_height = censusHeight; c.max_disp = maxDisp;
+    c.census_width = censusWidth; c.census_height = censusHeight; c.max_disp = (int32_t)std::min<uint32_t>(maxDisp, 1u << 20);
     c.bf_width = bfWidth; c.bf_height = bfHeight; c.p1 = p1; c.p2 = p2; c.uniq_ratio = uniqRatio;
     c.lr_max_diff = lrMaxDiff; c.mf_size = mfSize; c.b1 = b1; c.b2 = b2; c.b3 = b3;
     c.dilation = dilation; c.main_fx = mainFx; c.main_fy = mainFy; c.main_skew = mainSkew;
@@ -171,7 +175,7 @@ public:
                     f32_plane(mapRx, n, "map_rx", !rectified), f32_plane(mapRy, n, "map_ry", !rectified),
                     f32_plane(a1, n, "a1", true), f32_plane(a2, n, "a2", true), f32_plane(a3, n, "a3", true),
                     &e_));
-    rows_ = rows; cols_ = cols; batch_ = batch;
+    rows_ = rows; cols_ = cols; batch_ = batch; lead_ = (batch > 1 || batched) ? 1 : 0;
     check(ss_get_output_shape(e_, &orows_, &ocols_));
     check(ss_get_device(e_, &device_));
   }
@@ -191,7 +195,7 @@ public:
   void computeCuda(py::object leftObj, py::object rightObj, bool bbox, uint32_t x, uint32_t y,
                    uint32_t w, uint32_t h, py::object stream, bool sync) {
     CudaArray left = from_object(leftObj), right = from_object(rightObj);
-    const size_t lead = batch_ > 1 ? 1 : 0;
+    const size_t lead = lead_;
     if (left.shape.size() < 2 + lead || right.shape.size() < 2 + lead)
       throw std::runtime_error("Input image size different from initiated");
     if (left.shape[lead] != right.shape[lead] || left.shape[lead + 1] != right.shape[lead + 1])
@@ -204,15 +208,35 @@ public:
     if (!is_f4 && !is_u1) throw std::runtime_error("Input data type must be float");
     if (is_f4 && (left.shape.size() != 3 + lead || left.shape.back() != 4 || right.shape.size() != 3 + lead || right.shape.back() != 4))
       throw std::runtime_error("float input must be an RGBA image [H, W, 4]");
-    if (!left.contiguous() || !right.contiguous())
-      throw std::runtime_error("input CUDA arrays must be C-contiguous");
+    // Packed arrays, or pitched float RGBA views (a window of a BatchedCamera buffer, a sliced tensor): pixels
+    // must be 4 consecutive floats; row and environment pitches are free but common to both images.
+    bool pitched = false;
+    size_t env_pitch = 0, row_pitch = 0;
+    if (!left.contiguous() || !right.contiguous()) {
+      const size_t nd = left.shape.size();
+      bool ok = is_f4 && left.strides == right.strides && left.strides[nd - 1] == 4 && left.strides[nd - 2] == 16 &&
+                left.strides[nd - 3] >= (int64_t)cols_ * 16 && (!lead || left.strides[0] > 0);
+      if (!ok) throw std::runtime_error("input CUDA arrays must be C-contiguous, or float RGBA views with 16-byte pixels and equal pitches");
+      pitched = true;
+      row_pitch = (size_t)left.strides[nd - 3];
+      env_pitch = lead ? (size_t)left.strides[0] : row_pitch * rows_;
+    }
     if ((left.cuda_id >= 0 && left.cuda_id != device_) || (right.cuda_id >= 0 && right.cuda_id != device_))
       throw std::runtime_error("input CUDA arrays live on a different device than the engine");
     ss_bbox bb{bbox ? 1 : 0, x, y, w, h};
-    void *s = stream.is_none() ? nullptr : reinterpret_cast<void *>(stream.cast<uintptr_t>());
+    // stream=None does NOT mean "inputs are ready": the frame is ordered after the legacy default stream
+    // (where torch / cupy enqueue unless told otherwise) -- the reference orders by a device-wide sync at
+    // the start of the frame (core.cu:547).  Producer streams announced by the inputs themselves
+    // (__cuda_array_interface__ v3 `stream`) are honoured as well.  Pass stream=engine.cuda_stream to
+    // state that the inputs are complete and no ordering is wanted.
+    static constexpr uintptr_t kLegacy = 1;
+    void *s = reinterpret_cast<void *>(stream.is_none() ? kLegacy : stream.cast<uintptr_t>());
+    for (uintptr_t ps : {left.stream, right.stream})
+      if (ps && reinterpret_cast<void *>(ps) != s) check(ss_wait_stream(e_, reinterpret_cast<void *>(ps)));
     py::gil_scoped_release nogil;
-    int st = is_f4 ? ss_compute_device_rgba_f32(e_, left.ptr, right.ptr, &bb, s)
-                   : ss_compute_device_u8(e_, left.ptr, right.ptr, &bb, s);
+    int st = pitched ? ss_compute_device_rgba_f32_pitched(e_, left.ptr, right.ptr, env_pitch, row_pitch, &bb, s)
+             : is_f4 ? ss_compute_device_rgba_f32(e_, left.ptr, right.ptr, &bb, s)
+                     : ss_compute_device_u8(e_, left.ptr, right.ptr, &bb, s);
     if (!st && sync) st = ss_synchronize(e_);
     if (st) { py::gil_scoped_acquire gil; raise_status(st); }
   }
@@ -229,7 +253,11 @@ public:
       return out;
     }
     auto out = make_out({(py::ssize_t)orows_, (py::ssize_t)ocols_});
-    check(ss_get_depth_host(e_, out.mutable_data(), (size_t)out.nbytes()));
+    float *dst = out.mutable_data();
+    const size_t cap = (size_t)out.nbytes();
+    int st;
+    { py::gil_scoped_release nogil; st = ss_get_depth_host(e_, dst, cap); }
+    check(st);
     return out;
   }
   // extension: every following compute() streams its depth map into `out` (pinned float32 ndarray of
@@ -276,7 +304,8 @@ public:
   void setPenalties(int p1, int p2) { check(ss_set_penalties(e_, p1, p2)); }
   void setUniq(int u) { check(ss_set_uniqueness_ratio(e_, u)); }
   void setLr(int d) { check(ss_set_lr_max_diff(e_, d)); }
-  void synchronize() { check(ss_synchronize(e_)); }
+  void synchronize() { int st; { py::gil_scoped_release nogil; st = ss_synchronize(e_); } check(st); }
+  void waitStream(uintptr_t stream) { check(ss_wait_stream(e_, reinterpret_cast<void *>(stream))); }
   void setProfiling(bool on) { check(ss_set_profiling(e_, on)); }
   py::dict stageTimes() {
     const char *names[64]; float ms[64]; int32_t n = 0, frames = 0;
@@ -313,7 +342,7 @@ public:
 
 private:
   void checkHostShape(const U8 &l, const U8 &r) {
-    const size_t lead = batch_ > 1 ? 1 : 0;
+    const size_t lead = lead_;
     if (l.ndim() != (py::ssize_t)(2 + lead) || r.ndim() != (py::ssize_t)(2 + lead))
       throw std::runtime_error("Input image size different from initiated");
     for (int i = 0; i < l.ndim(); ++i)
@@ -323,18 +352,18 @@ private:
   }
   CudaArray checkedRgba(py::object rgba) {
     CudaArray a = from_object(rgba);
-    const size_t lead = batch_ > 1 ? 1 : 0;
+    const size_t lead = lead_;
     if (type_kind(a.type) != 'f' || item_size(a.type) != 4 || a.shape.size() != 3 + lead ||
         a.shape[lead] != orows_ || a.shape[lead + 1] != ocols_ || a.shape[lead + 2] != 4 || !a.contiguous())
       throw std::runtime_error("rgba must be a contiguous float32 CUDA array of shape [out_rows, out_cols, 4]");
     return a;
   }
   py::array_t<float> make_out(std::vector<py::ssize_t> shape) {
-    if (batch_ > 1) shape.insert(shape.begin(), batch_);
+    if (lead_) shape.insert(shape.begin(), batch_);
     return py::array_t<float>(shape);
   }
   CudaArray view(void *p, std::vector<int64_t> shape) {
-    if (batch_ > 1) shape.insert(shape.begin(), batch_);
+    if (lead_) shape.insert(shape.begin(), batch_);
     CudaArray a;
     a.shape = shape;
     a.strides.resize(shape.size());
@@ -349,6 +378,7 @@ private:
   uint32_t rows_ = 0, cols_ = 0, orows_ = 0, ocols_ = 0;
   int32_t device_ = 0;
   int batch_ = 1;
+  size_t lead_ = 0; // 1: inputs and outputs carry a leading environment dimension (batch > 1, or batched=True)
   py::object bound_ = py::none();
 };
 
@@ -395,17 +425,19 @@ PYBIND11_MODULE(_simsense_b200, m) {
 
   using E = DepthSensorEngine;
   py::class_<E>(m, "DepthSensorEngine")
+      // the ten small integers are uint8_t like python/pybind/simsense.cpp:54-73 (lr_max_diff stays int: the
+      // Python layer documents -1 as "off", which the reference's uint8_t wraps to 255)
       .def(py::init<uint32_t, uint32_t, uint32_t, uint32_t, float, float, float, float, uint64_t, float,
-                    float, float, float, bool, int, int, int, int, int, int, int, int, int, int, E::F32,
+                    float, float, float, bool, uint8_t, uint8_t, uint32_t, uint8_t, uint8_t, uint8_t, uint8_t, uint8_t, int, uint8_t, E::F32,
                     E::F32, E::F32, E::F32, E::F32, E::F32, E::F32, float, float, float, bool, float,
-                    float, float, float, float, int, int, bool>(),
+                    float, float, float, float, int, int, bool, bool>(),
            "rows"_a, "cols"_a, "rgb_rows"_a, "rgb_cols"_a, "focal_len"_a, "baseline_len"_a,
            "min_depth"_a, "max_depth"_a, "ir_noise_seed"_a, "speckle_shape"_a, "speckle_scale"_a,
            "gaussian_mu"_a, "gaussian_sigma"_a, "rectified"_a, "census_width"_a, "census_height"_a,
            "max_disp"_a, "bf_width"_a, "bf_height"_a, "p1"_a, "p2"_a, "uniq_ratio"_a, "lr_max_diff"_a,
            "mf_size"_a, "map_lx"_a, "map_ly"_a, "map_rx"_a, "map_ry"_a, "a1"_a, "a2"_a, "a3"_a, "b1"_a,
            "b2"_a, "b3"_a, "dilation"_a, "main_fx"_a, "main_fy"_a, "main_skew"_a, "main_cx"_a,
-           "main_cy"_a, "device"_a = -1, "batch"_a = 1, "keep_stages"_a = false)
+           "main_cy"_a, "device"_a = -1, "batch"_a = 1, "keep_stages"_a = false, "batched"_a = false)
       .def("compute", &E::computeHost, "left_array"_a, "right_array"_a, "bbox"_a = false,
            "bbox_start_x"_a = 0, "bbox_start_y"_a = 0, "bbox_width"_a = 0, "bbox_height"_a = 0)
       .def("compute", &E::computeCuda, "left_cuda"_a, "right_cuda"_a, "bbox"_a = false,
@@ -426,6 +458,7 @@ PYBIND11_MODULE(_simsense_b200, m) {
       .def("set_lr_max_diff", &E::setLr)
       // ---- extensions ----
       .def("synchronize", &E::synchronize)
+      .def("wait_stream", &E::waitStream, "stream"_a)
       .def("set_profiling", &E::setProfiling)
       .def("get_stage_times", &E::stageTimes)
       .def("get_launches_per_compute", &E::launches)

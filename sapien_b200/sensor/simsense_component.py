@@ -13,8 +13,11 @@ from typing import Optional, Union
 import numpy as np
 
 from ..pose import Pose
-from ..simsense import CudaArray, DepthSensorEngine
 from .calibration import calibrate
+
+# The native module (sapien_b200.simsense: DepthSensorEngine, CudaArray) is imported when the engine is
+# built, not at module import: the parameter validation, presets and calibration of this file are plain
+# host logic that test infrastructure may use without mapping the CUDA library.
 
 
 def _is_int(*vals) -> bool:
@@ -95,7 +98,7 @@ class SimSenseComponent:
         self._default_speckle_shape = self.DEFAULT_SPECKLE_SHAPE
         self._default_gaussian_sigma = self.DEFAULT_GAUSSIAN_SIGMA
         self._default_gaussian_mu = self.DEFAULT_GAUSSIAN_MU
-        self._engine: Optional[DepthSensorEngine] = None
+        self._engine = None  # sapien_b200.simsense.DepthSensorEngine once added to a scene
         self.calibration = None
 
     # -- noise parameters as the engine wants them (simsense_component.py:169-175) --------------
@@ -112,6 +115,8 @@ class SimSenseComponent:
         shape, scale, mu, sigma = self.noise_parameters()
         k = np.asarray(self.rgb_intrinsic, dtype=float)
         (iw, ih), (rw, rh) = self.ir_resolution, self.rgb_resolution
+        from ..simsense import DepthSensorEngine  # fails loudly without the CUDA extension: there is no CPU fallback
+
         self._engine = DepthSensorEngine(
             ih, iw, rh, rw, cal.focal_len, cal.baseline_len, self.min_depth, self.max_depth,
             self.ir_noise_seed, shape, scale, mu, sigma, self.rectified, self.census_width,
@@ -126,12 +131,12 @@ class SimSenseComponent:
     def on_remove_from_scene(self, scene=None) -> None:
         self._engine = None
 
-    def _eng(self) -> DepthSensorEngine:
+    def _eng(self):
         if self._engine is None:
             raise RuntimeError("simsense component is not added to scene")
         return self._engine
 
-    def compute(self, left: Union[np.ndarray, CudaArray], right: Union[np.ndarray, CudaArray],
+    def compute(self, left: Union[np.ndarray, "CudaArray"], right: Union[np.ndarray, "CudaArray"],
                 bbox_start: tuple = None, bbox_size: tuple = None) -> None:
         eng = self._eng()
         if bbox_start is not None and bbox_size is not None:
@@ -142,17 +147,17 @@ class SimSenseComponent:
     def get_ndarray(self) -> np.ndarray:
         return self._eng().get_ndarray()
 
-    def get_cuda(self) -> CudaArray:
+    def get_cuda(self) -> "CudaArray":
         return self._eng().get_cuda()
 
     def get_point_cloud_ndarray(self) -> np.ndarray:
         return self._eng().get_point_cloud_ndarray()
 
-    def get_point_cloud_cuda(self) -> CudaArray:
+    def get_point_cloud_cuda(self) -> "CudaArray":
         return self._eng().get_point_cloud_cuda()
 
     def get_rgb_point_cloud_ndarray(self, rgba_cuda) -> np.ndarray:
         return self._eng().get_rgb_point_cloud_ndarray(rgba_cuda)
 
-    def get_rgb_point_cloud_cuda(self, rgba_cuda) -> CudaArray:
+    def get_rgb_point_cloud_cuda(self, rgba_cuda) -> "CudaArray":
         return self._eng().get_rgb_point_cloud_cuda(rgba_cuda)

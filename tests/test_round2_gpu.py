@@ -1,0 +1,345 @@
+"""GPU parity tests added in round 2 (run with -m gpu on a B200): the production (keep_stages=False)
+kernels at the headline size, batched device-RGBA input, the sensor facade, the raw C ABI driven
+through ctypes, stream ordering of asynchronously produced inputs, the host-upload ordering of the
+generic census path, and env sharding with real engines."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import configs
+from sapien_b200 import synth
+from tests.common import assert_depth_close, assert_stages_equal, get_stage, make_engine, variant
+
+pytestmark = pytest.mark.gpu
+
+from oracle import REF_SO, RefEngine  # noqa: E402
+
+needs_ref = pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/libsimsense_ref.so not built")
+
+FAST_STAGES = ("census0", "census1", "cost", "disp_wta", "disp_right", "disp_med", "depth")
+
+
+def test_c1_production_kernels_vs_oracle(native, oracle):
+    """The instantiation bench.py times at C1 -- DBG=false templates, the 5-rows-per-block pinned-role
+    mapping of the final pass (720 rows / 148 SMs) and S3 aliasing L2 in place -- against the oracle:
+    cost volume, both WTA disparities, median, depth and the final map."""
+    prm = configs.params("C1")
+    left, right = configs.pair(prm, seed=0)
+    ref = oracle.pipeline(prm, left, right, volumes=True)
+    eng = make_engine(native, prm)  # keep_stages=False
+    eng.compute(left, right)
+    assert_stages_equal(eng, prm, ref, names=FAST_STAGES)
+    assert_depth_close(eng.get_ndarray(), ref["out"])
+    # device RGBA input (what bench.py's `value` feeds) gives the same bits as host u8
+    import torch
+
+    host = eng.get_ndarray().copy()
+    eng.compute(torch.from_numpy(synth.to_rgba(left)).cuda(), torch.from_numpy(synth.to_rgba(right)).cuda())
+    assert np.array_equal(eng.get_ndarray().view(np.uint32), host.view(np.uint32))
+
+
+@pytest.mark.parametrize("geom", [(160, 600, 128), (136, 740, 64), (200, 593, 96)])
+def test_five_rows_per_block_geometries_vs_oracle(native, oracle, geom):
+    """593..740 rows of one environment put 5 rows into every block of the final pass (pinned producer /
+    consumer roles): production kernels vs the oracle on narrow images of that height."""
+    cols, rows, d = geom
+    prm = configs._sensor_params("D415", max_disp=d, rectified=False, roll_deg=0.5,
+                                 scale=(cols, rows, (cols * 3) // 2, (rows * 3) // 2))
+    left, right = configs.pair(prm, seed=rows)
+    ref = oracle.pipeline(prm, left, right)
+    eng = make_engine(native, prm)
+    eng.compute(left, right)
+    assert_stages_equal(eng, prm, ref, names=FAST_STAGES)
+    assert_depth_close(eng.get_ndarray(), ref["out"])
+
+
+@pytest.mark.parametrize("cfg,n", [("C3", 3), ("C4", 5)])
+def test_batched_device_rgba_input_vs_oracle(native, oracle, cfg, n):
+    """[N,H,W,4] float32 CUDA batches (the BatchedCamera layout, and what bench.py feeds C3/C4/C5):
+    every environment of one batched call equals the oracle run on that environment alone."""
+    import torch
+
+    prm = configs.params(cfg)
+    pairs = [configs.pair(prm, seed=200 + s) for s in range(n)]
+    tl = torch.from_numpy(synth.to_rgba(np.stack([p[0] for p in pairs]))).cuda()
+    tr = torch.from_numpy(synth.to_rgba(np.stack([p[1] for p in pairs]))).cuda()
+    assert tuple(tl.shape) == (n, prm.rows, prm.cols, 4)
+    eng = make_engine(native, prm, batch=n)
+    eng.compute(tl, tr)
+    out = eng.get_cuda().torch().cpu().numpy()
+    assert out.shape == (n, prm.rgb_rows, prm.rgb_cols)
+    for i, (l, r) in enumerate(pairs):
+        ref = oracle.pipeline(prm, l, r, volumes=False)
+        assert_stages_equal(eng, prm, ref, names=("im0", "im1", "census0", "census1", "disp_wta", "disp_right", "disp_med", "depth"), index=i)
+        assert_depth_close(out[i], ref["out"], what=f"env {i}")
+
+
+def test_strided_batched_camera_view(native, oracle):
+    """BatchedCamera hands out [N,H,W,4] views with byte strides (batched_render_system.cpp:55-100): a view into a
+    larger allocation (row pitch and env pitch larger than the packed ones) must give the same result as the packed
+    copy."""
+    import torch
+
+    prm = configs.params("small435")
+    n = 3
+    pairs = [configs.pair(prm, seed=300 + s) for s in range(n)]
+    packed_l = torch.from_numpy(synth.to_rgba(np.stack([p[0] for p in pairs]))).cuda()
+    packed_r = torch.from_numpy(synth.to_rgba(np.stack([p[1] for p in pairs]))).cuda()
+    big_l = torch.full((n + 1, prm.rows + 3, prm.cols + 5, 4), -1.0, device="cuda")
+    big_r = torch.full((n + 1, prm.rows + 3, prm.cols + 5, 4), -1.0, device="cuda")
+    view_l = big_l[1:, 2:2 + prm.rows, 4:4 + prm.cols]
+    view_r = big_r[1:, 2:2 + prm.rows, 4:4 + prm.cols]
+    view_l.copy_(packed_l)
+    view_r.copy_(packed_r)
+    assert not view_l.is_contiguous()
+    eng = make_engine(native, prm, batch=n)
+    eng.compute(packed_l, packed_r)
+    want = eng.get_ndarray().copy()
+    eng.compute(view_l, view_r)
+    assert np.array_equal(eng.get_ndarray().view(np.uint32), want.view(np.uint32))
+    ref = oracle.pipeline(prm, *pairs[1], volumes=False)
+    assert_depth_close(want[1], ref["out"])
+    # a channel stride other than 4 bytes is not an image the renderer can produce: rejected, not misread
+    with pytest.raises(RuntimeError):
+        eng.compute(big_l[1:, :prm.rows, :prm.cols].transpose(2, 3)[..., :4], packed_r)
+
+
+def test_sensor_facade_on_gpu(native, oracle):
+    """StereoDepthSensor(StereoDepthSensorConfig("D415")) -> set_pictures -> compute_depth(bbox) -> get_depth /
+    get_pointcloud(with_rgb=True), against the oracle (python/py_package/sensor/stereodepth.py:294-475)."""
+    import torch
+
+    from sapien_b200.sensor import StereoDepthSensor, StereoDepthSensorConfig
+
+    cfg = StereoDepthSensorConfig("D415")
+    cfg.ir_speckle_noise = 0.0  # bit-exact parity: noise off (statistical parity is tested separately)
+    cfg.ir_thermal_noise = 0.0
+    cfg.max_disp = 64
+    sensor = StereoDepthSensor(cfg)
+    prm = configs._sensor_params("D415", max_disp=64, rectified=True)
+    left, right = configs.pair(prm, seed=4)
+    rgba = synth.make_rgb(prm.rgb_rows, prm.rgb_cols, 1)
+    rgba_t = torch.from_numpy(rgba).cuda()
+    with pytest.raises(RuntimeError):
+        sensor.take_picture()
+    sensor.set_pictures(torch.from_numpy(synth.to_rgba(left)).cuda(), torch.from_numpy(synth.to_rgba(right)).cuda(), rgba_t)
+    sensor.compute_depth()
+    ref = oracle.pipeline(prm, left, right, volumes=False)
+    assert_depth_close(sensor.get_depth(), ref["out"])
+    d_cuda = sensor.get_depth_cuda()
+    assert tuple(d_cuda.shape) == (1080, 1920) and d_cuda.typestr == "f4"
+    assert np.array_equal(d_cuda.torch().cpu().numpy().view(np.uint32), sensor.get_depth().view(np.uint32))
+    pc = sensor.get_pointcloud(with_rgb=True)
+    want = oracle.pointcloud(sensor.get_depth(), rgba, prm.main_fx, prm.main_fy, prm.main_skew, prm.main_cx, prm.main_cy)
+    np.testing.assert_allclose(pc, want, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(sensor.get_pointcloud_cuda().torch().cpu().numpy(), want[:, :3], rtol=1e-4, atol=1e-6)
+    # ROI compute (manualtest/stereodepth_bbox.py:118-119) with uint8 host pictures
+    sensor.set_pictures(left, right)
+    sensor.compute_depth(bbox_start=(100, 100), bbox_size=(640, 360))
+    ref_roi = oracle.pipeline(prm, left, right, bbox=(100, 100, 640, 360), volumes=False)
+    assert_depth_close(sensor.get_depth(), ref_roi["out"])
+    # runtime setters go through to the engine with the reference's validation
+    sensor.set_penalties(4, 60)
+    sensor.set_uniqueness_ratio(30)
+    sensor.compute_depth()
+    ref2 = oracle.pipeline(variant(prm, p1=4, p2=60, uniq_ratio=30), left, right, volumes=False)
+    assert_depth_close(sensor.get_depth(), ref2["out"])
+    with pytest.raises(TypeError):
+        sensor.set_penalties(60, 4)
+    assert sensor.get_config().p1_penalty == 4
+
+
+def test_raw_c_abi_compute_through_ctypes(native, oracle):
+    """The drop-in boundary itself: ss_create / ss_compute_host_u8 / ss_get_depth_host / ss_get_stage_host called
+    through ctypes with plain pointers (no pybind), against the oracle."""
+    from tests.test_cabi_cpu import LIB, SsConfig
+
+    lib = C.CDLL(LIB)
+    lib.ss_last_error.restype = C.c_char_p
+    prm = configs.params("small435")
+    left, right = configs.pair(prm, seed=21)
+    pl = prm.planes()
+    cfg = SsConfig(rows=prm.rows, cols=prm.cols, rgb_rows=prm.rgb_rows, rgb_cols=prm.rgb_cols, focal_len=prm.focal_len,
+                   baseline_len=prm.baseline_len, min_depth=prm.min_depth, max_depth=prm.max_depth, ir_noise_seed=0,
+                   rectified=int(prm.rectified), census_width=prm.census_width, census_height=prm.census_height,
+                   max_disp=prm.max_disp, bf_width=prm.bf_width, bf_height=prm.bf_height, p1=prm.p1, p2=prm.p2,
+                   uniq_ratio=prm.uniq_ratio, lr_max_diff=prm.lr_max_diff, mf_size=prm.mf_size, b1=prm.b1, b2=prm.b2,
+                   b3=prm.b3, dilation=int(prm.dilation), main_fx=prm.main_fx, main_fy=prm.main_fy,
+                   main_skew=prm.main_skew, main_cx=prm.main_cx, main_cy=prm.main_cy, registration=1, device=-1,
+                   batch=1, keep_stages=0)
+    fp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    eng = C.c_void_p()
+    rc = lib.ss_create(C.byref(cfg), None, None, None, None, fp(pl["a1"]), fp(pl["a2"]), fp(pl["a3"]), C.byref(eng))
+    assert rc == 0, lib.ss_last_error()
+    try:
+        out = np.empty((prm.rgb_rows, prm.rgb_cols), np.float32)
+        assert lib.ss_get_depth_host(eng, fp(out), C.c_size_t(out.nbytes)) == 2  # SS_ERR_NOT_COMPUTED
+        assert lib.ss_compute_host_u8(eng, fp(left), fp(right), None) == 0, lib.ss_last_error()
+        assert lib.ss_get_depth_host(eng, fp(out), C.c_size_t(out.nbytes)) == 0, lib.ss_last_error()
+        ref = oracle.pipeline(prm, left, right, volumes=False)
+        assert_depth_close(out, ref["out"])
+        dr = np.empty((prm.rows, prm.cols), np.uint16)
+        nbytes = C.c_size_t()
+        assert lib.ss_get_stage_host(eng, b"disp_right", 0, fp(dr), C.c_size_t(dr.nbytes), C.byref(nbytes)) == 0
+        assert nbytes.value == dr.nbytes and np.array_equal(dr, ref["disp_right"])
+        rows, cols = C.c_uint32(), C.c_uint32()
+        assert lib.ss_get_output_shape(eng, C.byref(rows), C.byref(cols)) == 0
+        assert (rows.value, cols.value) == (prm.rgb_rows, prm.rgb_cols)
+        small = np.empty(16, np.float32)
+        assert lib.ss_get_depth_host(eng, fp(small), C.c_size_t(small.nbytes)) == 1  # SS_ERR_INVALID: buffer too small
+    finally:
+        assert lib.ss_destroy(eng) == 0
+
+
+def test_inputs_produced_asynchronously_on_the_default_stream(native):
+    """compute(left_cuda, right_cuda) with the default stream=None must order the frame after work still queued
+    on the caller's (legacy default) stream -- the reference does a device-wide sync at the start of the frame
+    (core.cu:547).  The inputs are written by kernels queued BEHIND a long spin kernel."""
+    import torch
+
+    prm = configs.params("small435")
+    left, right = configs.pair(prm, seed=31)
+    eng = make_engine(native, prm)
+    eng.compute(left, right)
+    want = eng.get_ndarray().copy()
+    l8, r8 = torch.from_numpy(left).cuda(), torch.from_numpy(right).cuda()
+    tl = torch.zeros((prm.rows, prm.cols, 4), device="cuda")
+    tr = torch.zeros((prm.rows, prm.cols, 4), device="cuda")
+    torch.cuda.synchronize()
+    for rep in range(3):
+        tl.zero_()
+        tr.zero_()
+        torch.cuda._sleep(40_000_000)  # ~20 ms on the default stream
+        tl.copy_(((l8.float() + 0.5) / 255.0)[..., None].expand(-1, -1, 4))
+        tr.copy_(((r8.float() + 0.5) / 255.0)[..., None].expand(-1, -1, 4))
+        eng.compute(tl, tr, sync=False)       # host returns at once; the frame must wait for the copies above
+        got = eng.get_cuda().torch().clone()  # ... and the default stream for the frame (clone runs on it)
+        assert np.array_equal(got.cpu().numpy().view(np.uint32), want.view(np.uint32)), f"rep {rep}"
+    # a side stream announced through `stream=`
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        tl.zero_()
+        torch.cuda._sleep(40_000_000)
+        tl.copy_(((l8.float() + 0.5) / 255.0)[..., None].expand(-1, -1, 4))
+        eng.compute(tl, tr, stream=side.cuda_stream, sync=False)
+        got = eng.get_cuda().torch().clone()
+    side.synchronize()
+    assert np.array_equal(got.cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("census", [(5, 5), (9, 7)])
+def test_pinned_host_upload_is_ordered_before_the_generic_front_end(native, census):
+    """Host u8 compute with a census window other than 7x7: the uploads go to engine-owned buffers on the main stream
+    and the front-end runs on the helper stream -- it must wait for the DMA (pinned source, > 1 MB per image, so the
+    copy is truly asynchronous).  Compared with the same images given as device arrays."""
+    import torch
+
+    prm = variant(configs.params("C1"), census_width=census[0], census_height=census[1])
+    n = 2
+    pairs = [configs.pair(prm, seed=50 + i) for i in range(2 * n)]
+    eng = make_engine(native, prm, batch=n)
+    for k in range(2):
+        l = np.stack([pairs[2 * k + i][0] for i in range(n)])
+        r = np.stack([pairs[2 * k + i][1] for i in range(n)])
+        eng.compute(torch.from_numpy(l).cuda(), torch.from_numpy(r).cuda())
+        want = eng.get_ndarray().copy()
+        pl, pr = torch.from_numpy(l).pin_memory(), torch.from_numpy(r).pin_memory()
+        # poison the engine's upload buffers with the OTHER pair first, so stale data cannot pass
+        o = 1 - k
+        eng.compute(np.stack([pairs[2 * o + i][0] for i in range(n)]), np.stack([pairs[2 * o + i][1] for i in range(n)]))
+        eng.compute(pl.numpy(), pr.numpy())
+        assert np.array_equal(eng.get_ndarray().view(np.uint32), want.view(np.uint32)), f"pair set {k}"
+
+
+def test_sharded_stereo_depth_real_engines(native, oracle):
+    """ShardedStereoDepth with real engines in one process: a shard of exactly ONE environment keeps its leading
+    dimension, and pipelines=2 (two engines on their own streams) equals the single batched engine."""
+    import torch
+
+    from sapien_b200.sharding import ShardedStereoDepth
+
+    prm = configs.params("C4")
+    n = 5
+    pairs = [configs.pair(prm, seed=400 + s) for s in range(n)]
+    tl = torch.from_numpy(synth.to_rgba(np.stack([p[0] for p in pairs]))).cuda()
+    tr = torch.from_numpy(synth.to_rgba(np.stack([p[1] for p in pairs]))).cuda()
+    one = ShardedStereoDepth(prm.engine_args(), n_envs=1)
+    d1 = one.compute(tl[:1], tr[:1])
+    assert tuple(d1.shape) == (1, prm.rgb_rows, prm.rgb_cols)
+    ref0 = oracle.pipeline(prm, *pairs[0], volumes=False)
+    assert_depth_close(d1[0].cpu().numpy(), ref0["out"])
+    assert one.gather_depth(d1) is d1  # single process: identity
+    whole = ShardedStereoDepth(prm.engine_args(), n_envs=n)
+    piped = ShardedStereoDepth(prm.engine_args(), n_envs=n, pipelines=2)
+    assert [b - a for a, b in piped.blocks] == [3, 2]
+    a = whole.compute(tl, tr).clone()
+    b = piped.compute(tl, tr)
+    assert tuple(b.shape) == (n, prm.rgb_rows, prm.rgb_cols)
+    assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+    # rank 3 of 4 owns one environment of 5, rank 0 two: the blocks tile the batch
+    parts = []
+    for r in range(4):
+        sh = ShardedStereoDepth(prm.engine_args(), n_envs=n, rank=r, world=4)
+        parts.append(sh.compute(tl[sh.start:sh.stop], tr[sh.start:sh.stop]).clone())
+    assert torch.equal(torch.cat(parts).view(torch.int32), a.view(torch.int32))
+
+
+def _ks(a_u8: np.ndarray, b_u8: np.ndarray) -> float:
+    """Two-sample Kolmogorov-Smirnov statistic of two uint8 samples (from their histograms)."""
+    ca = np.cumsum(np.bincount(a_u8.ravel(), minlength=256)) / a_u8.size
+    cb = np.cumsum(np.bincount(b_u8.ravel(), minlength=256)) / b_u8.size
+    return float(np.abs(ca - cb).max())
+
+
+@needs_ref
+def test_ir_noise_statistical_parity_vs_reference(native):
+    """simInfraredNoise (camera.cu:21-75): speckle Gamma(shape, scale) * I + thermal N(mu, sigma), rounded and clamped.
+    The reference draws from per-pixel XORWOW states (48 B/pixel read and written back per image and frame); this
+    engine from a stateless Philox stream keyed by (seed, texel, frame).  Same distribution, different numbers:
+    compared on > 10^6 pixels per image -- per-intensity mean and variance, and a two-sample KS test on the noisy u8
+    histograms -- for constant images and for a textured one, stock parameters (simsense_component.py:160-175) and a
+    strong-noise setting (shape < 1 exercises the boost branch)."""
+    n = 1024
+    base = configs._sensor_params("D415", max_disp=32, rectified=True, scale=(n, n, n, n))
+    ks_crit = 1.95 * np.sqrt(2.0 / (n * n))  # alpha = 0.001
+    rng = np.random.Generator(np.random.PCG64(5))
+    tex = rng.integers(0, 256, size=(n, n), dtype=np.uint8)
+    flat = [np.full((n, n), v, np.uint8) for v in (0, 30, 120, 220, 255)]
+    for shape, scale, mu, sigma in ((1333.33, 1 / 1333.33, 0.0, 0.25), (40.0, 1 / 40.0, 1.5, 3.0), (0.7, 1 / 0.7, 0.0, 1.0)):
+        prm = variant(base, speckle_shape=shape, speckle_scale=scale, gaussian_mu=mu, gaussian_sigma=sigma, ir_noise_seed=1234)
+        ours = make_engine(native, prm)
+        ref = RefEngine(prm)
+        for img in flat + [tex]:
+            ours.compute(img, img)
+            ref.compute_host(img, img)
+            for side in (0, 1):
+                a = get_stage(ours, prm, f"im{side}")
+                b = ref.stage(f"noisyim{side}")
+                d = _ks(a, b)
+                assert d < ks_crit, f"shape={shape} image={int(img[0, 0]) if img is not tex else 'tex'} side={side}: KS {d:.5f} >= {ks_crit:.5f}"
+                if img is tex:  # per-intensity moments on the textured image
+                    src = img.ravel()
+                    cnt = np.bincount(src, minlength=256).astype(np.float64)
+                    for x in (a, b):
+                        x = x.ravel().astype(np.float64)
+                    fa, fb = a.ravel().astype(np.float64), b.ravel().astype(np.float64)
+                    ma = np.bincount(src, weights=fa, minlength=256) / cnt
+                    mb = np.bincount(src, weights=fb, minlength=256) / cnt
+                    va = np.bincount(src, weights=fa * fa, minlength=256) / cnt - ma * ma
+                    vb = np.bincount(src, weights=fb * fb, minlength=256) / cnt - mb * mb
+                    se = np.sqrt((va + vb) / cnt) + 1e-9  # standard error of the difference of the means
+                    assert np.all(np.abs(ma - mb) < 5.0 * se + 0.02), f"per-intensity means differ: max z {np.max(np.abs(ma - mb) / se):.2f}"
+                    assert np.all(np.abs(va - vb) < 0.08 * np.maximum(va, vb) + 0.05), "per-intensity variances differ"
+                else:
+                    fa, fb = a.astype(np.float64), b.astype(np.float64)
+                    se = np.sqrt((fa.var() + fb.var()) / a.size) + 1e-9
+                    assert abs(fa.mean() - fb.mean()) < 5.0 * se + 1e-3
+                    assert abs(fa.var() - fb.var()) < 0.02 * max(fa.var(), fb.var()) + 0.01
+        # the left and the right image use different streams, and successive frames too
+        ours.compute(tex, tex)
+        f1 = get_stage(ours, prm, "im0").copy()
+        ours.compute(tex, tex)
+        assert not np.array_equal(f1, get_stage(ours, prm, "im0")) and not np.array_equal(f1, get_stage(ours, prm, "im1"))
+        ref.close()

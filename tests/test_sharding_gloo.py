@@ -39,7 +39,10 @@ class FakeEngine:
         self.batch = batch
         self.out = None
 
-    def compute(self, left, right):
+    def synchronize(self):
+        pass
+
+    def compute(self, left, right, sync=True):
         assert left.shape[0] == self.batch
         self.out = (left.float().mean(dim=(1, 2))[:, None, None] + right.float()).contiguous()
 
@@ -47,17 +50,20 @@ class FakeEngine:
         return self.out
 
 
-def _worker(rank, world, port, n_envs, results):
+def _worker(rank, world, port, n_envs, results, pipelines=1):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         gen = torch.Generator().manual_seed(1234)
         left = torch.randint(0, 256, (n_envs, 6, 5), generator=gen, dtype=torch.uint8)
         right = torch.randint(0, 256, (n_envs, 6, 5), generator=gen, dtype=torch.uint8)
-        sh = sharding.ShardedStereoDepth((), n_envs, rank, world, engine_factory=FakeEngine)
-        local = sh.compute(left[sh.start:sh.stop], right[sh.start:sh.stop]) if sh.local else torch.zeros((0, 6, 5))
-        full = sh.gather_depth(local)  # all-gather
-        root = sh.gather_depth(local, dst=0)
+        sh = sharding.ShardedStereoDepth((), n_envs, rank, world, engine_factory=FakeEngine, pipelines=pipelines)
+        assert sum(b - a for a, b in sh.blocks) == sh.local and len(sh.engines) == min(pipelines, sh.local)
+        local = sh.compute(left[sh.start:sh.stop], right[sh.start:sh.stop])  # None on a rank without environments
+        assert (local is None) == (sh.local == 0)
+        like = ((6, 5), torch.float32, "cpu")
+        full = sh.gather_depth(local, like=like)  # all-gather
+        root = sh.gather_depth(local, dst=0, like=like)
         expect = left.float().mean(dim=(1, 2))[:, None, None] + right.float()
         ok = torch.equal(full, expect) and ((rank != 0 and root is None) or (rank == 0 and torch.equal(root, expect)))
         # timing reduction used by bench.py: max over ranks
@@ -75,12 +81,14 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world,n_envs", [(2, 8), (2, 5), (3, 7)])
-def test_sharded_compute_and_gather_over_gloo(world, n_envs):
+@pytest.mark.parametrize("world,n_envs,pipelines", [(2, 8, 1), (2, 5, 2), (3, 7, 1), (2, 2, 1), (3, 2, 3), (2, 1, 1)])
+def test_sharded_compute_and_gather_over_gloo(world, n_envs, pipelines):
+    """Even and uneven shards, sub-block pipelines, ranks that own exactly one environment (2, 2) and ranks that own
+    none (3 ranks / 2 envs, 2 ranks / 1 env): those join the gather with an empty tensor."""
     port = _free_port()
     mgr = mp.Manager()
     results = mgr.dict()
-    mp.spawn(_worker, args=(world, port, n_envs, results), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, n_envs, results, pipelines), nprocs=world, join=True)
     assert dict(results) == {r: True for r in range(world)}
 
 
