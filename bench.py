@@ -494,10 +494,36 @@ def run_ours(args, rank, world, local):
     ext_s = e2e_loop(ext_step)
     eng.bind_output(None)
     strict_s = e2e_loop(strict_step)
+
+    # (c) pipelined extension path: submit()/wait(), two frames in flight.  Every step still uploads its own inputs from
+    # pinned host memory and has its own depth map delivered into pinned host memory; the transfers of neighbouring
+    # frames overlap the compute (what a simulator loop that owns the sensor does).
+    outs = [out_np, torch.empty(out_shape, dtype=torch.float32).pin_memory().numpy()]
+    bbk = dict(zip(("bbox", "bbox_start_x", "bbox_start_y", "bbox_width", "bbox_height"), bb))
+
+    def piped(nsteps):
+        tk = [None, None]
+        for i in range(nsteps):
+            if tk[i % 2] is not None:
+                eng.wait(tk[i % 2])  # frame i-2 delivered: its output buffer may be reused
+            tk[i % 2] = eng.submit(pin_l[i % n_sets].numpy(), pin_r[i % n_sets].numpy(), out=outs[i % 2], **bbk)
+        for t in tk:
+            if t is not None:
+                eng.wait(t)
+
+    piped(4)
+    barrier(world)
+    t0 = time.perf_counter()
+    piped(e2e_steps)
+    torch.cuda.synchronize()
+    piped_s = max_over_ranks(time.perf_counter() - t0, world)
     h2d, d2h = int(2 * batch * prm.rows * prm.cols), int(out_np.nbytes)
-    e2e = {"value": batch * e2e_steps * world / ext_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "api": "extension path: DepthSensorEngine.bind_output(pinned) once; per step compute(left_u8 pinned, right_u8 pinned[, bbox]) + get_ndarray(out=pinned)",
+    e2e = {"value": batch * e2e_steps * world / piped_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "api": "extension path, pipelined: per step ticket = submit(left_u8 pinned, right_u8 pinned, out=pinned[, bbox]); wait(ticket of step-2): two frames in flight, "
+                  "every step's inputs uploaded and depth map delivered inside the timed region",
            "steps": e2e_steps,
+           "one_frame_at_a_time": {"value": batch * e2e_steps * world / ext_s, "unit": "frames/s",
+                                   "api": "extension path, synchronous: bind_output(pinned) once; per step compute(left_u8 pinned, right_u8 pinned[, bbox]) + get_ndarray(out=pinned)"},
            "strict": {"value": batch * e2e_steps * world / strict_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                       "api": "reference signature only: compute(left_u8 ndarray, right_u8 ndarray[, bbox]) + get_ndarray() -> new ndarray (pageable inputs, "
                              "engine-owned pinned staging, one host memcpy into the returned array)"}}

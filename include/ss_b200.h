@@ -72,6 +72,21 @@ typedef struct {
 int ss_create(const ss_config *cfg, const float *mapLx, const float *mapLy, const float *mapRx,
               const float *mapRy, const float *a1, const float *a2, const float *a3,
               ss_engine **out);
+/* Extension: calibration as MATRICES instead of seven H x W planes.  The reference generates the planes on
+ * the host (python/py_package/sensor/simsense_component.py:177-215 rectification maps through
+ * cv2.initUndistortRectifyMap, :308-325 registration planes) and reads them from HBM every frame; here
+ * the kernels evaluate them per pixel from the 3x3 matrices (row-major, float64):
+ *   registration  a(u,v) = reg_m * [u, v, 1]^T            (a1,a2,a3 = its three components, as float32)
+ *   rectification [X,Y,W] = rect_inv_* * [u, v, 1]^T,  map = (fx * X/W + cx, fy * Y/W + cy)
+ *                 with rect_inv_* = (P[:3,:3] * R)^-1 of that camera's stereoRectify result and
+ *                 (fx, fy, cx, cy) the undistorted IR camera matrix (no lens distortion, as in the reference call).
+ * No plane is uploaded, stored or read: -7 * rows * cols * 4 bytes of traffic per frame (26 MB at 1280x720). */
+typedef struct {
+  double reg_m[9];
+  double rect_inv_left[9], rect_inv_right[9]; /* ignored when cfg->rectified */
+  double ir_fx, ir_fy, ir_cx, ir_cy;
+} ss_calibration;
+int ss_create_calibrated(const ss_config *cfg, const ss_calibration *cal, ss_engine **out);
 /* E:80 / C:484-541 */
 int ss_destroy(ss_engine *e);
 
@@ -111,6 +126,16 @@ int ss_compute_device_rgba_f32_pitched(ss_engine *e, const void *left, const voi
 /* Extension: device uint8 [batch][rows][cols] pairs, same ordering rule. */
 int ss_compute_device_u8(ss_engine *e, const void *left, const void *right, const ss_bbox *bbox,
                          void *stream);
+/* Extension: ASYNCHRONOUS host-input frames.  ss_submit_host_u8 enqueues the uploads, the frame and the delivery of
+ * its depth map into out_host (float32 [batch][out_rows][out_cols]; page-locked for the transfers to overlap; may be
+ * NULL for "device result only") and returns at once with a ticket; ss_wait_frame blocks until that frame has been
+ * delivered.  Up to TWO frames are in flight: uploads and front-end of frame k+1 run while frame k aggregates, and the
+ * read-back of frame k runs under frame k+1 (inputs, outputs and the upload buffers are double-buffered inside the
+ * engine); a third submit first waits for the oldest frame.  left/right (and out_host) must stay valid until the
+ * frame's ticket has been waited for.  ss_compute_host_u8 is the synchronous form of the same path. */
+int ss_submit_host_u8(ss_engine *e, const uint8_t *left, const uint8_t *right, const ss_bbox *bbox,
+                      float *out_host, size_t capacity_bytes, uint64_t *ticket);
+int ss_wait_frame(ss_engine *e, uint64_t ticket);
 /* Extension: orders the NEXT compute of this engine after everything already enqueued on `stream`
  * (a producer stream other than the one passed to the compute call, e.g. the `stream` entry of a
  * __cuda_array_interface__ v3 input).  No host synchronisation. */

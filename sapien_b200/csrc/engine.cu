@@ -82,6 +82,18 @@ struct ss_engine {
   ss_config cfg{};
   int device = 0;
   cudaStream_t stream = nullptr, aux = nullptr, cpy = nullptr;
+  // host-input frames: uploads on `up` into double-buffered raw images, their front-ends on `fr`, so that the uploads
+  // and the front-end of frame k+1 overlap frame k (ss_submit_host_u8 keeps up to two frames in flight)
+  cudaStream_t up = nullptr, fr = nullptr;
+  cudaEvent_t ev_upL = nullptr, ev_upR = nullptr;
+  cudaEvent_t ev_lastband[2] = {nullptr, nullptr}; // column bands (helper stream) of the frame in slot s have finished
+  int band_slot = 0;
+  cudaEvent_t ev_rawfree[2] = {nullptr, nullptr}; // front-end that read raw slot s has finished
+  cudaEvent_t ev_done[2] = {nullptr, nullptr};    // host delivery of the frame in output slot s has finished
+  uint64_t slot_ticket[2] = {0, 0};               // ticket (frame number + 1) whose delivery ev_done[s] stands for, 0 = none
+  bool band_pending = false;                      // the last frame's column bands (helper stream) are not yet joined into the main stream
+  uint8_t *raw0s[2] = {nullptr, nullptr}, *raw1s[2] = {nullptr, nullptr};
+  float *out_pair[2] = {nullptr, nullptr};        // final depth of even / odd frames (a frame's read-back overlaps the next frame)
   cudaEvent_t ev[2] = {nullptr, nullptr};
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   cudaEvent_t ev_dep = nullptr; // ss_wait_stream: extra producer stream(s) the next compute is ordered after
@@ -102,6 +114,8 @@ struct ss_engine {
   std::vector<void *> allocs;
   float *mapLx = nullptr, *mapLy = nullptr, *mapRx = nullptr, *mapRy = nullptr;
   float *a1 = nullptr, *a2 = nullptr, *a3 = nullptr;
+  bool has_cal = false; // ss_create_calibrated: no planes, the kernels evaluate them from `cal`
+  ss_calibration cal{};
   uint8_t *raw0 = nullptr, *raw1 = nullptr, *im0 = nullptr, *im1 = nullptr;
   uint32_t *cen0 = nullptr, *cen1 = nullptr;
   uint16_t *C = nullptr, *L1 = nullptr, *L2 = nullptr, *S3 = nullptr;
@@ -163,9 +177,25 @@ int upload(ss_engine *e, float **dst, const float *src, size_t n) {
 int create_impl(ss_engine *e, const float *mapLx, const float *mapLy, const float *mapRx,
                 const float *mapRy, const float *a1, const float *a2, const float *a3) {
   const ss_config &c = e->cfg;
+  std::vector<float> ha1, ha3; // matrix calibration: host copies of a1 / a3, only for the banded-output bound below
+  if (e->has_cal && c.registration) {
+    const size_t n = (size_t)c.rows * c.cols;
+    ha1.resize(n); ha3.resize(n);
+    const double *m = e->cal.reg_m;
+    for (uint32_t v = 0; v < c.rows; ++v)
+      for (uint32_t u = 0; u < c.cols; ++u) {
+        ha1[(size_t)v * c.cols + u] = (float)((m[0] * u + m[1] * v) + m[2]);
+        ha3[(size_t)v * c.cols + u] = (float)((m[6] * u + m[7] * v) + m[8]);
+      }
+    a1 = ha1.data(); a3 = ha3.data();
+  }
   CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&e->cpy, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&e->up, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&e->fr, cudaStreamNonBlocking));
+  for (cudaEvent_t *ev : {&e->ev_upL, &e->ev_upR, &e->ev_lastband[0], &e->ev_lastband[1], &e->ev_rawfree[0], &e->ev_rawfree[1], &e->ev_done[0], &e->ev_done[1]})
+    CK(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
   for (auto &ev : e->ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto &ev : e->ev_seg) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto &ev : e->ev_band) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -177,14 +207,14 @@ int create_impl(ss_engine *e, const float *mapLx, const float *mapLy, const floa
   CK(cudaEventCreateWithFlags(&e->ev_dep, cudaEventDisableTiming));
   const size_t fsz = e->fsz(), N = (size_t)c.batch;
   int r;
-  if (!c.rectified) {
+  if (!c.rectified && !e->has_cal) {
     if (!mapLx || !mapLy || !mapRx || !mapRy) return fail(SS_ERR_INVALID, "rectification maps required when rectified is false");
     if ((r = upload(e, &e->mapLx, mapLx, fsz))) return r;
     if ((r = upload(e, &e->mapLy, mapLy, fsz))) return r;
     if ((r = upload(e, &e->mapRx, mapRx, fsz))) return r;
     if ((r = upload(e, &e->mapRy, mapRy, fsz))) return r;
   }
-  if (c.registration) {
+  if (c.registration && !e->has_cal) {
     if (!a1 || !a2 || !a3) return fail(SS_ERR_INVALID, "registration planes a1,a2,a3 required");
     if ((r = upload(e, &e->a1, a1, fsz))) return r;
     if ((r = upload(e, &e->a2, a2, fsz))) return r;
@@ -224,7 +254,7 @@ int create_impl(ss_engine *e, const float *mapLx, const float *mapLy, const floa
   const int nvol = c.keep_stages ? 7 : (fast0 ? 3 : 6);
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
-  const size_t small = N * (fsz * 40 + e->rsz() * 48) + (64u << 20);
+  const size_t small = N * (fsz * 42 + e->rsz() * 52) + (64u << 20);
   if (free_b < small + (size_t)nvol * vol) return fail(SS_ERR_CUDA, "not enough device memory for one frame");
   size_t budget = (size_t)((double)(free_b - small) * 0.6);
   e->wave = (int)std::min<size_t>(N, std::max<size_t>(1, budget / ((size_t)nvol * vol)));
@@ -238,8 +268,12 @@ int create_impl(ss_engine *e, const float *mapLx, const float *mapLy, const floa
   } else {
     e->S3 = e->L2;
   }
-  if ((r = e->alloc(&e->raw0, N * fsz))) return r;
-  if ((r = e->alloc(&e->raw1, N * fsz))) return r;
+  for (int k = 0; k < 2; ++k) {
+    if ((r = e->alloc(&e->raw0s[k], N * fsz))) return r;
+    if ((r = e->alloc(&e->raw1s[k], N * fsz))) return r;
+    if ((r = e->alloc(&e->out_pair[k], N * e->rsz()))) return r;
+  }
+  e->raw0 = e->raw0s[0]; e->raw1 = e->raw1s[0]; e->out = e->out_pair[0];
   if ((r = e->alloc(&e->im0, N * fsz))) return r;
   if ((r = e->alloc(&e->im1, N * fsz))) return r;
   if ((r = e->alloc(&e->cen0, N * fsz))) return r;
@@ -253,7 +287,6 @@ int create_impl(ss_engine *e, const float *mapLx, const float *mapLy, const floa
   if (c.registration && (r = e->alloc(&e->canvas_pair[0], N * e->rsz()))) return r;
   if (c.registration && (r = e->alloc(&e->canvas_pair[1], N * e->rsz()))) return r;
   e->canvas = e->canvas_pair[0];
-  if ((r = e->alloc(&e->out, N * e->rsz()))) return r;
   if ((r = e->alloc(&e->pc, N * e->rsz() * 3))) return r;
   if ((r = e->alloc(&e->rgbpc, N * e->rsz() * 6))) return r;
   CK(cudaStreamSynchronize(e->stream));
@@ -265,10 +298,13 @@ enum InputKind { IN_U8, IN_RGBA };
 // host_left / host_right: when non-null (host-u8 path, one wave, 7x7 census) the uploads happen here,
 // the right image on the helper stream, so that the left image's front-end overlaps the second upload
 // inputs_on_main: left/right are engine-owned buffers whose uploads were enqueued on the main stream
+// async_out: asynchronous host frame (ss_submit_host_u8): this frame's depth map goes to *async_out (may be null for
+// "no host delivery") and the main stream is NOT made to wait for the delivery -- ev_done[frame & 1] stands for it
 int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *right,
                  const ss_bbox *bbox, cudaStream_t user, const uint8_t *host_left = nullptr,
                  const uint8_t *host_right = nullptr, bool inputs_on_main = false,
-                 size_t env_pitch = 0, size_t row_pitch = 0) { // pitches in source elements, 0 = packed
+                 size_t env_pitch = 0, size_t row_pitch = 0, // pitches in source elements, 0 = packed
+                 bool async = false, float *async_out = nullptr) {
   NvtxRange nvtx_frame("ss_b200::compute");
   const ss_config &c = e->cfg;
   if (!left || !right) return fail(SS_ERR_INVALID, "null input image");
@@ -298,7 +334,19 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
   }
   e->mark("begin");
 
-  if (c.registration) e->canvas = e->canvas_pair[e->frame & 1];
+  const int slot = (int)(e->frame & 1);
+  if (c.registration) e->canvas = e->canvas_pair[slot];
+  e->out = e->out_pair[slot];
+  // the previous frame's column bands run on the helper stream; they read the disparity maps that this frame's final
+  // pass overwrites, so the main stream joins them right before that pass (and not earlier: the cost volume and the
+  // three plain passes of this frame overlap them)
+  auto join_prev_bands = [&]() -> int {
+    if (e->band_pending) {
+      CK(cudaStreamWaitEvent(st, e->ev_lastband[e->band_slot], 0));
+      e->band_pending = false;
+    }
+    return SS_OK;
+  };
   const int D = c.max_disp;
   const int P1 = c.p1 * c.bf_width * c.bf_height, P2 = c.p2 * c.bf_width * c.bf_height; // core.cu:670-671
   const int cmax = census_bits(c.census_width, c.census_height) * c.bf_width * c.bf_height;
@@ -311,7 +359,7 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
   bool banded = false;
   // Host-input frames have a host consumer: without a bound buffer they stream into the engine's own pinned
   // staging buffer and ss_get_depth_host copies from there (a pageable 8.3 MB cudaMemcpy costs ~2 ms at C1).
-  float *band_dst = e->host_out ? e->host_out : ((host_left || inputs_on_main) ? e->staging : nullptr);
+  float *band_dst = async ? async_out : (e->host_out ? e->host_out : ((host_left || inputs_on_main) ? e->staging : nullptr));
   if (band_dst && fast && !use_bbox && !c.keep_stages && c.batch <= e->wave &&
       (!c.registration || !e->rgb_sufmin.empty())) {
     // progress points (3, 4 and 5 points measured within 1 % of each other on C1: the copy engine is the bound --
@@ -340,6 +388,12 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
       fp.right_rgba = static_cast<const float *>(right) + (size_t)w0 * fp.src_env;
     }
     fp.mapLx = e->mapLx; fp.mapLy = e->mapLy; fp.mapRx = e->mapRx; fp.mapRy = e->mapRy;
+    if (e->has_cal && !c.rectified) {
+      fp.cal_maps = 1;
+      std::memcpy(fp.rinvL, e->cal.rect_inv_left, sizeof(fp.rinvL));
+      std::memcpy(fp.rinvR, e->cal.rect_inv_right, sizeof(fp.rinvR));
+      fp.ir_fx = e->cal.ir_fx; fp.ir_fy = e->cal.ir_fy; fp.ir_cx = e->cal.ir_cx; fp.ir_cy = e->cal.ir_cy;
+    }
     fp.frows = (int)c.rows; fp.fcols = (int)c.cols; fp.bx = bx; fp.by = by;
     fp.rows = rows; fp.cols = cols; fp.cw = c.census_width; fp.ch = c.census_height; fp.N = wn;
     fp.im0 = e->im0 + (size_t)w0 * msz; fp.im1 = e->im1 + (size_t)w0 * msz;
@@ -354,17 +408,27 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
     {
     NvtxRange nvtx_front("front");
     if (host_left) {
+      // Host images: uploaded on the upload stream into raw slot `slot` (the front-end that last read it, two frames
+      // ago, has finished), each image's front-end on the front stream as soon as its upload has landed and the
+      // previous frame no longer needs the census buffers -- i.e. while the previous frame is still aggregating.
       const size_t bytes = (size_t)c.batch * fsz;
-      CK(cudaEventRecord(e->ev[0], st)); // the helper stream starts behind whatever precedes this frame
-      CK(cudaStreamWaitEvent(e->aux, e->ev[0], 0));
-      CK(cudaMemcpyAsync(e->raw0, host_left, bytes, cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync(e->raw1, host_right, bytes, cudaMemcpyHostToDevice, e->aux));
+      fp.left_u8 = e->raw0s[slot]; fp.right_u8 = e->raw1s[slot];
+      CK(cudaStreamWaitEvent(e->up, e->ev_rawfree[slot], 0));
+      CK(cudaMemcpyAsync(e->raw0s[slot], host_left, bytes, cudaMemcpyHostToDevice, e->up));
+      CK(cudaEventRecord(e->ev_upL, e->up));
+      CK(cudaMemcpyAsync(e->raw1s[slot], host_right, bytes, cudaMemcpyHostToDevice, e->up));
+      CK(cudaEventRecord(e->ev_upR, e->up));
+      CK(cudaStreamWaitEvent(e->fr, e->ev_cost, 0)); // (first frame: never recorded, no-op)
+      CK(cudaStreamWaitEvent(e->fr, e->ev_lastband[slot], 0)); // the dilation that last read this slot's splat canvas (two frames ago)
+      CK(cudaStreamWaitEvent(e->fr, e->ev_upL, 0));
       fp.only_image = 0;
-      CK(launch_front(fp, st));
+      CK(launch_front(fp, e->fr));
+      CK(cudaStreamWaitEvent(e->fr, e->ev_upR, 0));
       fp.only_image = 1; fp.canvas = nullptr;
-      CK(launch_front(fp, e->aux));
-      CK(cudaEventRecord(e->ev[1], e->aux));
-      CK(cudaStreamWaitEvent(st, e->ev[1], 0));
+      CK(launch_front(fp, e->fr));
+      CK(cudaEventRecord(e->ev_front, e->fr));
+      CK(cudaEventRecord(e->ev_rawfree[slot], e->fr));
+      CK(cudaStreamWaitEvent(st, e->ev_front, 0));
       ++launches;
     } else if (c.batch <= e->wave) {
       // Device inputs, one wave: the front-end runs on the helper stream and only waits until the previous
@@ -405,6 +469,7 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
       CK(launch_aggr_passes(ab, wn, rows, cols, D, P1, P2, c.uniq_ratio, st, e->aux, e->ev, e->profiling ? &am : nullptr));
       launches += 3;
       if (!banded) { // (banded: the final pass follows below, with its progress counters)
+        { int r = join_prev_bands(); if (r) return r; }
         CK(launch_aggr_final(ab, wn, rows, cols, D, P1, P2, c.uniq_ratio, st, nullptr, 0, nullptr));
         e->mark("aggr_right_wta");
         launches += 1;
@@ -414,6 +479,7 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
       if (c.batch <= e->wave) CK(cudaEventRecord(e->ev_cost, st));
       launches += 2;
     } else {
+      { int r = join_prev_bands(); if (r) return r; }
       CK(launch_aggr_wta_generic(ab, nullptr, wn, rows, cols, D, P1, P2, c.uniq_ratio, st));
       if (c.batch <= e->wave) CK(cudaEventRecord(e->ev_cost, st));
       launches += 8;
@@ -432,6 +498,7 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
   pp.depth = e->depth;
   pp.registration = c.registration; pp.dilation = c.dilation;
   pp.a1 = e->a1; pp.a2 = e->a2; pp.a3 = e->a3; pp.b1 = c.b1; pp.b2 = c.b2; pp.b3 = c.b3;
+  if (e->has_cal) std::memcpy(pp.reg_m, e->cal.reg_m, sizeof(pp.reg_m));
   pp.rgb_rows = (int)c.rgb_rows; pp.rgb_cols = (int)c.rgb_cols;
   pp.canvas = e->canvas; pp.out = e->out;
   pp.canvas_prefilled = 1;
@@ -446,6 +513,8 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
     ab.dispL = e->dispL; ab.dispR = e->dispR;
     const int H = c.mf_size / 2, ocols = (int)e->out_cols(), orows = (int)e->out_rows();
     const size_t pitch = (size_t)ocols * sizeof(float);
+    { int r = join_prev_bands(); if (r) return r; } // (also: nobody polls the progress counters any more)
+    CK(cudaStreamWaitEvent(e->aux, e->ev_done[slot], 0)); // the read-back of the frame that last used this output slot
     CK(cudaMemsetAsync(e->progress, 0, ss_engine::MAXSEG * sizeof(uint32_t), st));
     CK(cudaEventRecord(e->ev_seg[0], st));
     CK(cudaStreamWaitEvent(e->aux, e->ev_seg[0], 0)); // counters are zero before anybody waits on them
@@ -482,16 +551,28 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
       xa = xb; ua = ub;
     }
     e->mark("aggr_right_wta");
-    CK(cudaEventRecord(e->ev_copied, e->cpy));
-    CK(cudaStreamWaitEvent(st, e->ev_band[nseg], 0));
-    CK(cudaStreamWaitEvent(st, e->ev_copied, 0));
+    CK(cudaEventRecord(e->ev_lastband[slot], e->aux));
+    CK(cudaEventRecord(e->ev_done[slot], e->cpy));
+    e->band_pending = true;
+    e->band_slot = slot;
+    if (!async) { // synchronous callers: completion of the main stream means "delivered"
+      int r = join_prev_bands(); if (r) return r;
+      CK(cudaStreamWaitEvent(st, e->ev_done[slot], 0));
+    }
     e->streamed = true;
     e->stream_dst = band_dst;
   } else {
     int pl = 0;
     CK(launch_post(pp, st, &pl));
     launches += pl;
+    if (async) { // no column bands for this configuration: one copy behind the frame
+      if (async_out) CK(cudaMemcpyAsync(async_out, e->out, (size_t)c.batch * e->rsz() * sizeof(float), cudaMemcpyDeviceToHost, st));
+      CK(cudaEventRecord(e->ev_done[slot], st));
+      e->streamed = async_out != nullptr;
+      e->stream_dst = async_out;
+    }
   }
+  if (async) e->slot_ticket[slot] = e->frame + 1;
   e->mark("post");
   e->launches = launches;
   e->mrows = rows; e->mcols = cols;
@@ -506,14 +587,46 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
 
 } // namespace
 
+// Host-facing calls that read results through the main stream first join whatever an asynchronous frame left on the
+// helper and copy streams (its column bands and their copies).
+static int join_async(ss_engine *e) {
+  if (e->band_pending) {
+    CK(cudaStreamWaitEvent(e->stream, e->ev_lastband[e->band_slot], 0));
+    CK(cudaStreamWaitEvent(e->stream, e->ev_done[e->band_slot], 0));
+    e->band_pending = false;
+  }
+  return SS_OK;
+}
+
 extern "C" {
 
 const char *ss_last_error(void) { return g_err.c_str(); }
 const char *ss_version(void) { return "ss_b200 0.1 (sm_100a)"; }
 
+static int create_common(const ss_config *cfg, const ss_calibration *cal, const float *mapLx, const float *mapLy,
+                         const float *mapRx, const float *mapRy, const float *a1, const float *a2, const float *a3,
+                         ss_engine **out);
+
 int ss_create(const ss_config *cfg, const float *mapLx, const float *mapLy, const float *mapRx,
               const float *mapRy, const float *a1, const float *a2, const float *a3,
               ss_engine **out) {
+  return create_common(cfg, nullptr, mapLx, mapLy, mapRx, mapRy, a1, a2, a3, out);
+}
+
+int ss_create_calibrated(const ss_config *cfg, const ss_calibration *cal, ss_engine **out) {
+  if (!cal) return fail(SS_ERR_INVALID, "null calibration");
+  for (double v : cal->reg_m) if (!std::isfinite(v)) return fail(SS_ERR_INVALID, "registration matrix is not finite");
+  if (cfg && !cfg->rectified) {
+    for (int i = 0; i < 9; ++i)
+      if (!std::isfinite(cal->rect_inv_left[i]) || !std::isfinite(cal->rect_inv_right[i])) return fail(SS_ERR_INVALID, "rectification matrix is not finite");
+    if (!(cal->ir_fx > 0) || !(cal->ir_fy > 0)) return fail(SS_ERR_INVALID, "IR focal lengths must be positive");
+  }
+  return create_common(cfg, cal, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, out);
+}
+
+static int create_common(const ss_config *cfg, const ss_calibration *cal, const float *mapLx, const float *mapLy,
+                         const float *mapRx, const float *mapRy, const float *a1, const float *a2, const float *a3,
+                         ss_engine **out) {
   if (!cfg || !out) return fail(SS_ERR_INVALID, "null argument");
   *out = nullptr;
   int r = validate_params(*cfg);
@@ -536,6 +649,7 @@ int ss_create(const ss_config *cfg, const float *mapLx, const float *mapLy, cons
   if (e->cfg.lr_max_diff == -1) e->cfg.lr_max_diff = 255; // uint8_t wrap in the reference ctor
   e->device = dev;
   e->cfg.device = dev;
+  if (cal) { e->has_cal = true; e->cal = *cal; }
   r = create_impl(e, mapLx, mapLy, mapRx, mapRy, a1, a2, a3);
   if (r) { std::string keep = g_err; ss_destroy(e); g_err = keep; return r; }
   *out = e;
@@ -547,6 +661,7 @@ int ss_destroy(ss_engine *e) {
   DeviceGuard g(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->aux) cudaStreamSynchronize(e->aux);
+  if (e->cpy) cudaStreamSynchronize(e->cpy);
   for (void *p : e->allocs) cudaFree(p);
   if (e->staging) cudaFreeHost(e->staging);
   for (auto ev : e->pev) cudaEventDestroy(ev);
@@ -554,6 +669,10 @@ int ss_destroy(ss_engine *e) {
   for (auto ev : e->ev_seg) if (ev) cudaEventDestroy(ev);
   for (auto ev : e->ev_band) if (ev) cudaEventDestroy(ev);
   if (e->ev_copied) cudaEventDestroy(e->ev_copied);
+  for (cudaEvent_t ev : {e->ev_upL, e->ev_upR, e->ev_lastband[0], e->ev_lastband[1], e->ev_rawfree[0], e->ev_rawfree[1], e->ev_done[0], e->ev_done[1]})
+    if (ev) cudaEventDestroy(ev);
+  if (e->up) { cudaStreamSynchronize(e->up); cudaStreamDestroy(e->up); }
+  if (e->fr) { cudaStreamSynchronize(e->fr); cudaStreamDestroy(e->fr); }
   if (e->ev_cost) cudaEventDestroy(e->ev_cost);
   if (e->ev_front) cudaEventDestroy(e->ev_front);
   if (e->cpy) { cudaStreamSynchronize(e->cpy); cudaStreamDestroy(e->cpy); }
@@ -626,9 +745,45 @@ int ss_wait_stream(ss_engine *e, void *stream) {
   return SS_OK;
 }
 
+int ss_submit_host_u8(ss_engine *e, const uint8_t *left, const uint8_t *right, const ss_bbox *bbox, float *out_host,
+                      size_t capacity_bytes, uint64_t *ticket) {
+  if (!e || !left || !right || !ticket) return fail(SS_ERR_INVALID, "null argument");
+  if (out_host && capacity_bytes < (size_t)e->cfg.batch * e->rsz() * sizeof(float)) return fail(SS_ERR_INVALID, "output buffer too small");
+  DeviceGuard g(e->device);
+  const int slot = (int)(e->frame & 1);
+  if (e->slot_ticket[slot]) { // at most two frames in flight: the frame that last used this slot must have been delivered
+    CK(cudaEventSynchronize(e->ev_done[slot]));
+    e->slot_ticket[slot] = 0;
+  }
+  const size_t bytes = (size_t)e->cfg.batch * e->fsz();
+  const bool split = e->cfg.census_width == 7 && e->cfg.census_height == 7 && e->cfg.batch <= e->wave;
+  if (!split) { // generic census / multi-wave batches: uploads and frame on the main stream (asynchronous, not overlapped)
+    CK(cudaMemcpyAsync(e->raw0, left, bytes, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->raw1, right, bytes, cudaMemcpyHostToDevice, e->stream));
+  }
+  int r = compute_impl(e, IN_U8, e->raw0, e->raw1, bbox, nullptr, split ? left : nullptr, split ? right : nullptr, !split, 0, 0,
+                       true, out_host);
+  if (r) return r;
+  *ticket = e->frame; // (compute_impl has advanced the frame counter: ticket = frame number + 1)
+  return SS_OK;
+}
+
+int ss_wait_frame(ss_engine *e, uint64_t ticket) {
+  if (!e) return fail(SS_ERR_INVALID, "null engine");
+  if (ticket == 0 || ticket > e->frame) return fail(SS_ERR_INVALID, "unknown frame ticket");
+  DeviceGuard g(e->device);
+  const int slot = (int)((ticket - 1) & 1);
+  if (e->slot_ticket[slot] == ticket) { // (an older ticket of this slot was already waited for by a later submit)
+    CK(cudaEventSynchronize(e->ev_done[slot]));
+    e->slot_ticket[slot] = 0;
+  }
+  return SS_OK;
+}
+
 int ss_synchronize(ss_engine *e) {
   if (!e) return fail(SS_ERR_INVALID, "null engine");
   DeviceGuard g(e->device);
+  { int r = join_async(e); if (r) return r; }
   CK(cudaStreamSynchronize(e->stream));
   return SS_OK;
 }
@@ -666,6 +821,7 @@ int ss_get_depth_host(ss_engine *e, float *out, size_t cap) {
   if (!e) return fail(SS_ERR_INVALID, "null engine");
   if (!e->computed) return fail(SS_ERR_NOT_COMPUTED, "No computed data stored");
   DeviceGuard g(e->device);
+  { int r = join_async(e); if (r) return r; }
   const size_t bytes = (size_t)e->cfg.batch * e->rsz() * sizeof(float);
   if (e->streamed && out && out == e->stream_dst) { // already delivered band by band during compute
     CK(cudaStreamSynchronize(e->stream));
@@ -684,6 +840,7 @@ int ss_bind_output_host(ss_engine *e, float *out, size_t cap) {
   if (!e) return fail(SS_ERR_INVALID, "null engine");
   if (out && cap < (size_t)e->cfg.batch * e->rsz() * sizeof(float)) return fail(SS_ERR_INVALID, "output buffer too small");
   DeviceGuard g(e->device);
+  { int r = join_async(e); if (r) return r; }
   CK(cudaStreamSynchronize(e->stream)); // a frame may still be streaming into the previous binding
   e->host_out = out;
   e->host_cap = out ? cap : 0;
@@ -694,11 +851,13 @@ int ss_bind_output_host(ss_engine *e, float *out, size_t cap) {
 int ss_get_depth_device(ss_engine *e, void **ptr) {
   if (!e || !ptr) return fail(SS_ERR_INVALID, "null argument");
   if (!e->computed) return fail(SS_ERR_NOT_COMPUTED, "No computed data stored");
+  if (e->band_pending) { DeviceGuard g(e->device); int r = join_async(e); if (r) return r; }
   *ptr = e->out;
   return SS_OK;
 }
 static int run_pc(ss_engine *e, const void *rgba) {
   const ss_config &c = e->cfg;
+  { int r = join_async(e); if (r) return r; }
   if (rgba) { // the colour image may still be in flight on the caller's (default) stream
     CK(cudaEventRecord(e->ev_in, cudaStreamLegacy));
     CK(cudaStreamWaitEvent(e->stream, e->ev_in, 0));
@@ -770,6 +929,7 @@ int ss_get_stage_host(ss_engine *e, const char *name, int32_t index, void *out, 
   if (!e->computed) return fail(SS_ERR_NOT_COMPUTED, "No computed data stored");
   if (index < 0 || index >= e->cfg.batch) return fail(SS_ERR_INVALID, "batch index out of range");
   DeviceGuard g(e->device);
+  { int r = join_async(e); if (r) return r; }
   const std::string n(name);
   const size_t msz = (size_t)e->mrows * e->mcols, fsz = e->fsz(), D = (size_t)e->cfg.max_disp;
   const void *src = nullptr;

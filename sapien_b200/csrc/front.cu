@@ -89,14 +89,34 @@ struct Src {
   const float *mapx, *mapy;
 };
 
+// Rectification map of pixel (u, v) from matrices (ss_create_calibrated): what cv2.initUndistortRectifyMap(K, None,
+// R, P, size, CV_32F) tabulates -- [X,Y,W] = (P[:3,:3] R)^-1 [u,v,1]^T, map = K (X/W, Y/W) -- in float64, rounded to
+// float32 like the CV_32F planes.
+__device__ __forceinline__ void cal_map(const FrontParams &p, int img, int u, int v, float &mx, float &my) {
+  const double *m = img ? p.rinvR : p.rinvL;
+  const double du = (double)u, dv = (double)v;
+  const double X = __dadd_rn(__dadd_rn(__dmul_rn(du, m[0]), __dmul_rn(dv, m[1])), m[2]);
+  const double Y = __dadd_rn(__dadd_rn(__dmul_rn(du, m[3]), __dmul_rn(dv, m[4])), m[5]);
+  const double W = __dadd_rn(__dadd_rn(__dmul_rn(du, m[6]), __dmul_rn(dv, m[7])), m[8]);
+  const double iw = 1.0 / W;
+  mx = (float)__fma_rn(p.ir_fx, X * iw, p.ir_cx);
+  my = (float)__fma_rn(p.ir_fy, Y * iw, p.ir_cy);
+}
+
 template <bool RGBA>
 __device__ __forceinline__ int fetch(const FrontParams &p, const Src &s, int n, int y, int x,
                                      int which) {
   if (x < 0 || x >= p.cols || y < 0 || y >= p.rows) return 0; // zero padding (csct.cu:40-42)
   int fx = x + p.bx, fy = y + p.by;
-  if (s.mapx) {
-    const size_t mp = (size_t)fy * p.fcols + fx;
-    float sx = roundf(__ldg(s.mapx + mp)), sy = roundf(__ldg(s.mapy + mp));
+  if (s.mapx || p.cal_maps) {
+    float mx, my;
+    if (p.cal_maps) {
+      cal_map(p, which, fx, fy, mx, my);
+    } else {
+      const size_t mp = (size_t)fy * p.fcols + fx;
+      mx = __ldg(s.mapx + mp); my = __ldg(s.mapy + mp);
+    }
+    float sx = roundf(mx), sy = roundf(my);
     sx = fminf(fmaxf(sx, 0.0f), (float)(p.fcols - 1));
     sy = fminf(fmaxf(sy, 0.0f), (float)(p.frows - 1));
     fx = (int)sx; fy = (int)sy;
@@ -218,7 +238,8 @@ template <int I, int J> struct CensusBits {
 // the map -> texel gather, not by bandwidth).
 // PITCHED: the source rows / environments are not packed (FrontParams::src_row / src_env); the packed
 // instantiation keeps its tighter address arithmetic (the kernel sits at its register cap).
-template <bool RGBA, int MINB, bool PITCHED>
+// CALMAP: rectification maps evaluated from matrices (FrontParams::cal_maps) instead of read from planes.
+template <bool RGBA, int MINB, bool PITCHED, bool CALMAP>
 __global__ void __launch_bounds__(F7_NT, MINB) front7_kernel(const FrontParams p) {
   __shared__ __align__(16) uint32_t win[1][F7_WH][F7_WB / 4];
   const int tid = threadIdx.x;
@@ -263,7 +284,9 @@ __global__ void __launch_bounds__(F7_NT, MINB) front7_kernel(const FrontParams p
         inside[k] = x >= 0 && x < p.cols && y >= 0 && y < p.rows;
         fx[k] = min(max(x, 0), p.cols - 1) + p.bx;
         fy[k] = min(max(y, 0), p.rows - 1) + p.by;
-        if (s.mapx) {
+        if (CALMAP) {
+          cal_map(p, img, fx[k], fy[k], mx[k], my[k]);
+        } else if (s.mapx) {
           const size_t mp = (size_t)fy[k] * p.fcols + fx[k];
           mx[k] = __ldg(s.mapx + mp);
           my[k] = __ldg(s.mapy + mp);
@@ -274,7 +297,7 @@ __global__ void __launch_bounds__(F7_NT, MINB) front7_kernel(const FrontParams p
       uint32_t sp[HALF]; // packed: texel index inside environment n; PITCHED: element offset (one image is < 4 Gi elements)
 #pragma unroll
       for (int k = 0; k < HALF; ++k) {
-        if (s.mapx) { // camera.cu:83-119: always-snapped nearest neighbour
+        if (CALMAP || s.mapx) { // camera.cu:83-119: always-snapped nearest neighbour
           const float sx = fminf(fmaxf(roundf(mx[k]), 0.0f), (float)(p.fcols - 1));
           const float sy = fminf(fmaxf(roundf(my[k]), 0.0f), (float)(p.frows - 1));
           fx[k] = (int)sx; fy[k] = (int)sy;
@@ -345,12 +368,15 @@ cudaError_t launch_front(const FrontParams &p, cudaStream_t st) {
     const dim3 grid((p.cols + F7_TW - 1) / F7_TW, (p.rows + F7_TH - 1) / F7_TH, (p.only_image < 0 ? 2 : 1) * p.N);
     const bool packed = p.left_rgba ? (p.src_row == 4u * (uint32_t)p.fcols && p.src_env == 4 * (size_t)p.frows * p.fcols)
                                     : (p.src_row == (uint32_t)p.fcols && p.src_env == (size_t)p.frows * p.fcols);
+    // (the pitched and the matrix-map variants are the general instantiation: <.., PITCHED = true, CALMAP>)
     if (p.left_rgba) {
-      if (packed) front7_kernel<true, 4, false><<<grid, F7_NT, 0, st>>>(p);
-      else front7_kernel<true, 4, true><<<grid, F7_NT, 0, st>>>(p);
+      if (p.cal_maps) front7_kernel<true, 3, true, true><<<grid, F7_NT, 0, st>>>(p);
+      else if (packed) front7_kernel<true, 4, false, false><<<grid, F7_NT, 0, st>>>(p);
+      else front7_kernel<true, 4, true, false><<<grid, F7_NT, 0, st>>>(p);
     } else {
-      if (packed) front7_kernel<false, 4, false><<<grid, F7_NT, 0, st>>>(p);
-      else front7_kernel<false, 4, true><<<grid, F7_NT, 0, st>>>(p);
+      if (p.cal_maps) front7_kernel<false, 3, true, true><<<grid, F7_NT, 0, st>>>(p);
+      else if (packed) front7_kernel<false, 4, false, false><<<grid, F7_NT, 0, st>>>(p);
+      else front7_kernel<false, 4, true, false><<<grid, F7_NT, 0, st>>>(p);
     }
     return cudaGetLastError();
   }

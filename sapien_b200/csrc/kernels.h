@@ -16,7 +16,12 @@ struct FrontParams {
   // Packed inputs: frows*fcols(*4) and fcols(*4).  A float RGBA pixel is always 4 consecutive floats.
   size_t src_env;
   uint32_t src_row;
-  const float *mapLx, *mapLy, *mapRx, *mapRy; // null when rectified
+  const float *mapLx, *mapLy, *mapRx, *mapRy; // null when rectified (or when the maps are evaluated from matrices)
+  // matrix calibration (ss_create_calibrated): when cal_maps != 0 the rectification map of a pixel is evaluated
+  // in double from rect_inv_* and the IR camera matrix instead of being read from the planes above
+  int cal_maps;
+  double rinvL[9], rinvR[9];
+  double ir_fx, ir_fy, ir_cx, ir_cy;
   int frows, fcols;                           // full IR size
   int bx, by;                                 // ROI origin (0,0 when no bbox)
   int rows, cols;                             // matched (ROI) size
@@ -94,7 +99,8 @@ struct PostParams {
   float *depth;            // [N][frows][fcols]
   // registration
   int registration, dilation;
-  const float *a1, *a2, *a3; // [frows][fcols]
+  const float *a1, *a2, *a3; // [frows][fcols]; all null: a(u,v) = reg_m * [u,v,1]^T evaluated per pixel
+  double reg_m[9];
   float b1, b2, b3;
   int rgb_rows, rgb_cols;
   float *canvas;   // [N][rgb_rows][rgb_cols] splat target

@@ -57,14 +57,24 @@ __device__ __forceinline__ float atomic_min_float(float *addr, float value) { //
 
 // disparity -> depth (camera.cu:160-168) and, with registration, the forward splat into the RGB
 // frame (camera.cu:179-196); same expression shapes as the reference so nvcc contracts identically.
-__device__ __forceinline__ void depth_and_splat(const PostParams &p, size_t n, size_t pos, float d) {
+// (u, v) = full-image pixel coordinates of `pos`
+__device__ __forceinline__ void depth_and_splat(const PostParams &p, size_t n, size_t pos, int u, int v, float d) {
   const size_t idx = n * (size_t)p.frows * p.fcols + pos;
   const float z = (d <= 0) ? 0 : p.focal * p.baseline / d;
   p.depth[idx] = z;
   if (p.registration) {
-    const float zRgb = p.a3[pos] * z + p.b3;
-    const int x = (int)roundf((p.a1[pos] * z + p.b1) / zRgb);
-    const int y = (int)roundf((p.a2[pos] * z + p.b2) / zRgb);
+    float a1, a2, a3;
+    if (p.a1) {
+      a1 = p.a1[pos]; a2 = p.a2[pos]; a3 = p.a3[pos];
+    } else { // the float64 products and sums of simsense_component.py:308-325, rounded to float32 like the plane upload
+      const double du = (double)u, dv = (double)v;
+      a1 = (float)__dadd_rn(__dadd_rn(__dmul_rn(p.reg_m[0], du), __dmul_rn(p.reg_m[1], dv)), p.reg_m[2]);
+      a2 = (float)__dadd_rn(__dadd_rn(__dmul_rn(p.reg_m[3], du), __dmul_rn(p.reg_m[4], dv)), p.reg_m[5]);
+      a3 = (float)__dadd_rn(__dadd_rn(__dmul_rn(p.reg_m[6], du), __dmul_rn(p.reg_m[7], dv)), p.reg_m[8]);
+    }
+    const float zRgb = a3 * z + p.b3;
+    const int x = (int)roundf((a1 * z + p.b1) / zRgb);
+    const int y = (int)roundf((a2 * z + p.b2) / zRgb);
     if (zRgb > 0 && x >= 0 && x < p.rgb_cols && y >= 0 && y < p.rgb_rows)
       atomic_min_float(p.canvas + (n * p.rgb_rows + y) * p.rgb_cols + x, zRgb);
   } else {
@@ -161,7 +171,7 @@ __global__ void __launch_bounds__(PT_X *PT_Y) lr_median_kernel(const PostParams 
     }
   }
   p.disp_med[img + (size_t)y * p.cols + x] = out;
-  if (FUSE) depth_and_splat(p, (size_t)n, (size_t)y * p.cols + x, out);
+  if (FUSE) depth_and_splat(p, (size_t)n, (size_t)y * p.cols + x, x, y, out);
   else if (p.bbox) p.disp_full[((size_t)n * p.frows + (y + p.by)) * p.fcols + x + p.bx] = out;
 }
 
@@ -177,7 +187,9 @@ __global__ void __launch_bounds__(256) depth_splat_kernel(const PostParams p) { 
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= fsz * p.N) return;
   const size_t n = idx / fsz;
-  depth_and_splat(p, n, idx - n * fsz, p.disp_full[idx]);
+  const size_t pos = idx - n * fsz;
+  const int v = (int)(pos / p.fcols);
+  depth_and_splat(p, n, pos, (int)(pos - (size_t)v * p.fcols), v, p.disp_full[idx]);
 }
 
 // Dilation with snapshot semantics + range clamp, canvas -> out.

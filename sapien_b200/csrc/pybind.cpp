@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -158,7 +159,7 @@ public:
                     uint8_t bfHeight, uint8_t p1, uint8_t p2, uint8_t uniqRatio, int lrMaxDiff, uint8_t mfSize, F32 mapLx,
                     F32 mapLy, F32 mapRx, F32 mapRy, F32 a1, F32 a2, F32 a3, float b1, float b2,
                     float b3, bool dilation, float mainFx, float mainFy, float mainSkew, float mainCx,
-                    float mainCy, int device, int batch, bool keepStages, bool batched) {
+                    float mainCy, int device, int batch, bool keepStages, bool batched, py::object calibration) {
     ss_config c{};
     c.rows = rows; c.cols = cols; c.rgb_rows = rgbRows; c.rgb_cols = rgbCols;
     c.focal_len = focalLen; c.baseline_len = baselineLen; c.min_depth = minDepth; c.max_depth = maxDepth;
@@ -171,10 +172,31 @@ public:
     c.main_cx = mainCx; c.main_cy = mainCy; c.registration = 1;
     c.device = device; c.batch = batch; c.keep_stages = keepStages;
     const size_t n = (size_t)rows * cols;
-    check(ss_create(&c, f32_plane(mapLx, n, "map_lx", !rectified), f32_plane(mapLy, n, "map_ly", !rectified),
-                    f32_plane(mapRx, n, "map_rx", !rectified), f32_plane(mapRy, n, "map_ry", !rectified),
-                    f32_plane(a1, n, "a1", true), f32_plane(a2, n, "a2", true), f32_plane(a3, n, "a3", true),
-                    &e_));
+    if (!calibration.is_none()) {
+      // extension: calibration=(reg_m 3x3, rect_inv_left 3x3, rect_inv_right 3x3, (fx, fy, cx, cy)) float64 -- the planes
+      // are evaluated in the kernels; the seven plane arguments are ignored (pass empty arrays)
+      using F64 = py::array_t<double, py::array::c_style | py::array::forcecast>;
+      auto t = calibration.cast<py::tuple>();
+      if (t.size() != 4) throw py::type_error("calibration must be (reg_m, rect_inv_left, rect_inv_right, (fx, fy, cx, cy))");
+      ss_calibration cal{};
+      auto m3 = [](py::handle h, double (&dst)[9], const char *name) {
+        auto a = h.cast<F64>();
+        if (a.size() != 9) throw py::type_error(std::string(name) + " must be a 3x3 matrix");
+        std::memcpy(dst, a.data(), sizeof(dst));
+      };
+      m3(t[0], cal.reg_m, "reg_m");
+      m3(t[1], cal.rect_inv_left, "rect_inv_left");
+      m3(t[2], cal.rect_inv_right, "rect_inv_right");
+      auto k = t[3].cast<F64>();
+      if (k.size() != 4) throw py::type_error("ir camera must be (fx, fy, cx, cy)");
+      cal.ir_fx = k.data()[0]; cal.ir_fy = k.data()[1]; cal.ir_cx = k.data()[2]; cal.ir_cy = k.data()[3];
+      check(ss_create_calibrated(&c, &cal, &e_));
+    } else {
+      check(ss_create(&c, f32_plane(mapLx, n, "map_lx", !rectified), f32_plane(mapLy, n, "map_ly", !rectified),
+                      f32_plane(mapRx, n, "map_rx", !rectified), f32_plane(mapRy, n, "map_ry", !rectified),
+                      f32_plane(a1, n, "a1", true), f32_plane(a2, n, "a2", true), f32_plane(a3, n, "a3", true),
+                      &e_));
+    }
     rows_ = rows; cols_ = cols; batch_ = batch; lead_ = (batch > 1 || batched) ? 1 : 0;
     check(ss_get_output_shape(e_, &orows_, &ocols_));
     check(ss_get_device(e_, &device_));
@@ -190,6 +212,30 @@ public:
     py::gil_scoped_release nogil;
     int st = ss_compute_host_u8(e_, l, r, &bb);
     if (st) { py::gil_scoped_acquire gil; raise_status(st); }
+  }
+  // extension: asynchronous host frames (ss_submit_host_u8 / ss_wait_frame).  The arrays are kept alive until waited for.
+  uint64_t submitHost(U8 left, U8 right, py::object out_arg, bool bbox, uint32_t x, uint32_t y, uint32_t w, uint32_t h) {
+    checkHostShape(left, right);
+    float *dst = nullptr;
+    size_t cap = 0;
+    if (!out_arg.is_none()) {
+      auto out = out_arg.cast<py::array_t<float, py::array::c_style>>();
+      if (out.ptr() != out_arg.ptr()) throw py::type_error("out must be a C-contiguous float32 ndarray");
+      dst = out.mutable_data();
+      cap = (size_t)out.nbytes();
+    }
+    ss_bbox bb{bbox ? 1 : 0, x, y, w, h};
+    uint64_t ticket = 0;
+    check(ss_submit_host_u8(e_, left.data(), right.data(), &bb, dst, cap, &ticket));
+    inflight_[ticket] = py::make_tuple(left, right, out_arg);
+    while (inflight_.size() > 2) inflight_.erase(inflight_.begin()); // older frames were waited for inside submit
+    return ticket;
+  }
+  void waitFrame(uint64_t ticket) {
+    int st;
+    { py::gil_scoped_release nogil; st = ss_wait_frame(e_, ticket); }
+    check(st);
+    inflight_.erase(ticket);
   }
   // python/pybind/simsense.cpp:83-99
   void computeCuda(py::object leftObj, py::object rightObj, bool bbox, uint32_t x, uint32_t y,
@@ -380,6 +426,7 @@ private:
   int batch_ = 1;
   size_t lead_ = 0; // 1: inputs and outputs carry a leading environment dimension (batch > 1, or batched=True)
   py::object bound_ = py::none();
+  std::map<uint64_t, py::object> inflight_;
 };
 
 } // namespace
@@ -430,14 +477,14 @@ PYBIND11_MODULE(_simsense_b200, m) {
       .def(py::init<uint32_t, uint32_t, uint32_t, uint32_t, float, float, float, float, uint64_t, float,
                     float, float, float, bool, uint8_t, uint8_t, uint32_t, uint8_t, uint8_t, uint8_t, uint8_t, uint8_t, int, uint8_t, E::F32,
                     E::F32, E::F32, E::F32, E::F32, E::F32, E::F32, float, float, float, bool, float,
-                    float, float, float, float, int, int, bool, bool>(),
+                    float, float, float, float, int, int, bool, bool, py::object>(),
            "rows"_a, "cols"_a, "rgb_rows"_a, "rgb_cols"_a, "focal_len"_a, "baseline_len"_a,
            "min_depth"_a, "max_depth"_a, "ir_noise_seed"_a, "speckle_shape"_a, "speckle_scale"_a,
            "gaussian_mu"_a, "gaussian_sigma"_a, "rectified"_a, "census_width"_a, "census_height"_a,
            "max_disp"_a, "bf_width"_a, "bf_height"_a, "p1"_a, "p2"_a, "uniq_ratio"_a, "lr_max_diff"_a,
            "mf_size"_a, "map_lx"_a, "map_ly"_a, "map_rx"_a, "map_ry"_a, "a1"_a, "a2"_a, "a3"_a, "b1"_a,
            "b2"_a, "b3"_a, "dilation"_a, "main_fx"_a, "main_fy"_a, "main_skew"_a, "main_cx"_a,
-           "main_cy"_a, "device"_a = -1, "batch"_a = 1, "keep_stages"_a = false, "batched"_a = false)
+           "main_cy"_a, "device"_a = -1, "batch"_a = 1, "keep_stages"_a = false, "batched"_a = false, "calibration"_a = py::none())
       .def("compute", &E::computeHost, "left_array"_a, "right_array"_a, "bbox"_a = false,
            "bbox_start_x"_a = 0, "bbox_start_y"_a = 0, "bbox_width"_a = 0, "bbox_height"_a = 0)
       .def("compute", &E::computeCuda, "left_cuda"_a, "right_cuda"_a, "bbox"_a = false,
@@ -457,6 +504,9 @@ PYBIND11_MODULE(_simsense_b200, m) {
       .def("set_uniqueness_ratio", &E::setUniq)
       .def("set_lr_max_diff", &E::setLr)
       // ---- extensions ----
+      .def("submit", &E::submitHost, "left_array"_a, "right_array"_a, "out"_a = py::none(), "bbox"_a = false,
+           "bbox_start_x"_a = 0, "bbox_start_y"_a = 0, "bbox_width"_a = 0, "bbox_height"_a = 0)
+      .def("wait", &E::waitFrame, "ticket"_a)
       .def("synchronize", &E::synchronize)
       .def("wait_stream", &E::waitStream, "stream"_a)
       .def("set_profiling", &E::setProfiling)

@@ -40,9 +40,18 @@ class Calibration:
     a2: np.ndarray
     a3: np.ndarray
     b: np.ndarray
+    # the same calibration as 3x3 float64 matrices (DepthSensorEngine(calibration=...)): the engine then evaluates
+    # the planes per pixel and none of the seven H x W arrays above is uploaded or read
+    reg_m: np.ndarray = None          # K_rgb R_(ir->rgb) K_ir^-1: a(u,v) = reg_m [u,v,1]^T
+    rect_inv_l: np.ndarray = None     # (P1[:3,:3] R1)^-1
+    rect_inv_r: np.ndarray = None     # (P2[:3,:3] R2)^-1
+    ir_camera: tuple = None           # (fx, fy, cx, cy) of the IR camera matrix
+
+    def matrices(self):
+        return (self.reg_m, self.rect_inv_l, self.rect_inv_r, self.ir_camera)
 
 
-def calibrate(ir_size, rgb_size, k_ir, k_rgb, pose_l: Pose, pose_r: Pose) -> Calibration:
+def calibrate(ir_size, rgb_size, k_ir, k_rgb, pose_l: Pose, pose_r: Pose, planes: bool = True) -> Calibration:
     """ir_size / rgb_size are (width, height).  Same OpenCV calls and arguments as the reference
     (stereoRectify alpha=1, initUndistortRectifyMap CV_32F), simsense_component.py:177-215."""
     import cv2
@@ -58,7 +67,14 @@ def calibrate(ir_size, rgb_size, k_ir, k_rgb, pose_l: Pose, pose_r: Pose) -> Cal
     r1, r2, p1, p2, q, _, _ = cv2.stereoRectify(
         cameraMatrix1=k_ir, distCoeffs1=None, cameraMatrix2=k_ir, distCoeffs2=None,
         imageSize=tuple(ir_size), R=l2r[:3, :3], T=l2r[:3, 3:], alpha=1.0, newImageSize=tuple(ir_size))
+    reg_m = k_rgb @ l2rgb[:3, :3] @ np.linalg.inv(k_ir)
+    mats = dict(reg_m=reg_m, rect_inv_l=np.linalg.inv(p1[:3, :3] @ r1), rect_inv_r=np.linalg.inv(p2[:3, :3] @ r2),
+                ir_camera=(float(k_ir[0][0]), float(k_ir[1][1]), float(k_ir[0][2]), float(k_ir[1][2])))
+    if not planes:  # matrices only: no H x W array is generated (cv2 is used for the 3x3 stereoRectify alone)
+        empty = np.zeros((0,), np.float32)
+        b = (k_rgb @ l2rgb[:3, 3:]).reshape(3)
+        return Calibration(float(q[2][3]), float(1.0 / q[3][2]), empty, empty, empty, empty, empty, empty, empty, b, **mats)
     map_lx, map_ly = cv2.initUndistortRectifyMap(k_ir, None, r1, p1, tuple(ir_size), cv2.CV_32F)
     map_rx, map_ry = cv2.initUndistortRectifyMap(k_ir, None, r2, p2, tuple(ir_size), cv2.CV_32F)
     a1, a2, a3, b = registration_planes(ir_size, k_ir, k_rgb, l2rgb)
-    return Calibration(float(q[2][3]), float(1.0 / q[3][2]), map_lx, map_ly, map_rx, map_ry, a1, a2, a3, b)
+    return Calibration(float(q[2][3]), float(1.0 / q[3][2]), map_lx, map_ly, map_rx, map_ry, a1, a2, a3, b, **mats)

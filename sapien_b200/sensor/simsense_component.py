@@ -65,7 +65,7 @@ class SimSenseComponent:
                  rectified: bool, census_width: int, census_height: int, max_disp: int, block_width: int,
                  block_height: int, p1_penalty: int, p2_penalty: int, uniqueness_ratio: int,
                  lr_max_diff: int, median_filter_size: int, depth_dilation: bool, *, device: int = -1,
-                 batch: int = 1, keep_stages: bool = False):
+                 batch: int = 1, keep_stages: bool = False, device_calibration: bool = True):
         validate_parameters(rgb_resolution, ir_resolution, ir_speckle_noise, ir_thermal_noise, census_width,
                             census_height, max_disp, block_width, block_height, p1_penalty, p2_penalty,
                             uniqueness_ratio, lr_max_diff, median_filter_size)
@@ -95,6 +95,9 @@ class SimSenseComponent:
         self.device = device
         self.batch = batch
         self.keep_stages = keep_stages
+        # True: the engine gets the calibration as 3x3 matrices and evaluates the rectification maps and the
+        # registration planes per pixel; False: the reference's seven H x W planes (simsense_component.py:177-215,308-325)
+        self.device_calibration = device_calibration
         self._default_speckle_shape = self.DEFAULT_SPECKLE_SHAPE
         self._default_gaussian_sigma = self.DEFAULT_GAUSSIAN_SIGMA
         self._default_gaussian_mu = self.DEFAULT_GAUSSIAN_MU
@@ -110,7 +113,7 @@ class SimSenseComponent:
 
     def on_add_to_scene(self, scene=None) -> None:
         cal = calibrate(self.ir_resolution, self.rgb_resolution, self.ir_intrinsic, self.rgb_intrinsic,
-                        self.trans_pose_l, self.trans_pose_r)
+                        self.trans_pose_l, self.trans_pose_r, planes=not self.device_calibration)
         self.calibration = cal
         shape, scale, mu, sigma = self.noise_parameters()
         k = np.asarray(self.rgb_intrinsic, dtype=float)
@@ -124,7 +127,8 @@ class SimSenseComponent:
             self.p2_penalty, self.uniqueness_ratio, self.lr_max_diff, self.median_filter_size,
             cal.map_lx, cal.map_ly, cal.map_rx, cal.map_ry, cal.a1, cal.a2, cal.a3,
             cal.b[0], cal.b[1], cal.b[2], self.depth_dilation, k[0][0], k[1][1], k[0][1], k[0][2], k[1][2],
-            device=self.device, batch=self.batch, keep_stages=self.keep_stages)
+            device=self.device, batch=self.batch, keep_stages=self.keep_stages,
+            calibration=cal.matrices() if self.device_calibration else None)
 
     build = on_add_to_scene
 

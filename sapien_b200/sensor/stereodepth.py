@@ -82,7 +82,7 @@ class StereoDepthSensorConfig:
 
 class StereoDepthSensor:
     def __init__(self, config: StereoDepthSensorConfig, mount=None, pose: Pose = Pose(), *,
-                 device: int = -1, batch: int = 1, keep_stages: bool = False):
+                 device: int = -1, batch: int = 1, keep_stages: bool = False, device_calibration: bool = True):
         self._config = config
         self._mount = mount
         self._pose = pose
@@ -92,7 +92,8 @@ class StereoDepthSensor:
             c.trans_pose_r, c.min_depth, c.max_depth, c.ir_noise_seed, c.ir_speckle_noise,
             c.ir_thermal_noise, c.rectified, c.census_width, c.census_height, c.max_disp, c.block_width,
             c.block_height, c.p1_penalty, c.p2_penalty, c.uniqueness_ratio, c.lr_max_diff,
-            c.median_filter_size, c.depth_dilation, device=device, batch=batch, keep_stages=keep_stages)
+            c.median_filter_size, c.depth_dilation, device=device, batch=batch, keep_stages=keep_stages,
+            device_calibration=device_calibration)
         self._ss.on_add_to_scene(None)
         self._left = self._right = self._rgba = None
 

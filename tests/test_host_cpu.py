@@ -128,3 +128,39 @@ def test_algorithmic_bytes_match_the_survey_table():
     assert abs(configs.algorithmic_bytes(configs.params("C5"), rgba_input=True) / 10.92e9 - 1) < 0.02
     c2 = configs.algorithmic_bytes(configs.params("C2"), rgba_input=True, bbox=configs.BBOX_C2, point_cloud="xyzrgb")
     assert abs(c2 / 0.818e9 - 1) < 0.02
+
+
+@pytest.mark.parametrize("model,roll", [("D415", 0.0), ("D435", 0.0), ("D415", 0.5)])
+def test_matrix_calibration_reproduces_the_planes(model, roll):
+    """Device-side calibration (ss_create_calibrated) evaluates per pixel what the reference tabulates on the host
+    (simsense_component.py:177-215, 308-325).  Emulated here with the kernels' float64 operation order: the
+    registration planes come out byte-identical as float32; the rectification maps agree with cv2's CV_32F planes to
+    float32 rounding of values near zero and give the SAME nearest-neighbour source pixel everywhere (remap snaps
+    every coordinate, camera.cu:83-119)."""
+    import math
+
+    c = StereoDepthSensorConfig(model)
+    pose_r = c.trans_pose_r
+    if roll:
+        a = math.radians(roll) / 2
+        pose_r = pose_r * Pose([0, 0, 0], [math.cos(a), math.sin(a), 0, 0])
+    cal = calibrate(c.ir_resolution, c.rgb_resolution, c.ir_intrinsic, c.rgb_intrinsic, c.trans_pose_l, pose_r)
+    only = calibrate(c.ir_resolution, c.rgb_resolution, c.ir_intrinsic, c.rgb_intrinsic, c.trans_pose_l, pose_r, planes=False)
+    assert only.a1.size == 0 and only.map_lx.size == 0 and np.array_equal(only.reg_m, cal.reg_m) and np.array_equal(only.b, cal.b)
+    w, h = c.ir_resolution
+    u, v = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
+    m = cal.reg_m
+    for i, plane in enumerate((cal.a1, cal.a2, cal.a3)):
+        mine = ((m[i, 0] * u + m[i, 1] * v) + m[i, 2]).astype(np.float32)
+        assert np.array_equal(mine.view(np.uint32), plane.astype(np.float32).view(np.uint32)), f"a{i + 1}"
+    fx, fy, cx, cy = cal.ir_camera
+    for inv, mx, my in ((cal.rect_inv_l, cal.map_lx, cal.map_ly), (cal.rect_inv_r, cal.map_rx, cal.map_ry)):
+        X = (u * inv[0, 0] + v * inv[0, 1]) + inv[0, 2]
+        Y = (u * inv[1, 0] + v * inv[1, 1]) + inv[1, 2]
+        W = (u * inv[2, 0] + v * inv[2, 1]) + inv[2, 2]
+        iw = 1.0 / W
+        gx, gy = (fx * (X * iw) + cx).astype(np.float32), (fy * (Y * iw) + cy).astype(np.float32)
+        assert np.abs(gx - mx).max() < 1e-4 and np.abs(gy - my).max() < 1e-4
+        assert (gx.view(np.uint32) != mx.view(np.uint32)).mean() < 2e-3  # (only the ~0 entries of column / row 0 differ)
+        snap = lambda a, hi: np.clip(np.sign(a) * np.floor(np.abs(a) + 0.5), 0, hi)  # noqa: E731  roundf + clamp
+        assert np.array_equal(snap(gx, w - 1), snap(mx, w - 1)) and np.array_equal(snap(gy, h - 1), snap(my, h - 1))

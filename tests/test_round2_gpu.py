@@ -322,8 +322,6 @@ def test_ir_noise_statistical_parity_vs_reference(native):
                 if img is tex:  # per-intensity moments on the textured image
                     src = img.ravel()
                     cnt = np.bincount(src, minlength=256).astype(np.float64)
-                    for x in (a, b):
-                        x = x.ravel().astype(np.float64)
                     fa, fb = a.ravel().astype(np.float64), b.ravel().astype(np.float64)
                     ma = np.bincount(src, weights=fa, minlength=256) / cnt
                     mb = np.bincount(src, weights=fb, minlength=256) / cnt
@@ -331,7 +329,11 @@ def test_ir_noise_statistical_parity_vs_reference(native):
                     vb = np.bincount(src, weights=fb * fb, minlength=256) / cnt - mb * mb
                     se = np.sqrt((va + vb) / cnt) + 1e-9  # standard error of the difference of the means
                     assert np.all(np.abs(ma - mb) < 5.0 * se + 0.02), f"per-intensity means differ: max z {np.max(np.abs(ma - mb) / se):.2f}"
-                    assert np.all(np.abs(va - vb) < 0.08 * np.maximum(va, vb) + 0.05), "per-intensity variances differ"
+                    # ~4 100 pixels per intensity: a variance estimate has relative standard error ~sqrt(2/n)
+                    tol = 6.0 * np.sqrt(2.0 / cnt) * np.sqrt(2.0) * np.maximum(va, vb) + 0.05
+                    assert np.all(np.abs(va - vb) < tol), f"per-intensity variances differ: worst {np.max(np.abs(va - vb) / tol):.2f} x tolerance"
+                    # pooled over all intensities the two variances agree much more tightly
+                    assert abs(va.mean() - vb.mean()) < 0.01 * max(va.mean(), vb.mean()) + 0.01
                 else:
                     fa, fb = a.astype(np.float64), b.astype(np.float64)
                     se = np.sqrt((fa.var() + fb.var()) / a.size) + 1e-9
@@ -343,3 +345,144 @@ def test_ir_noise_statistical_parity_vs_reference(native):
         ours.compute(tex, tex)
         assert not np.array_equal(f1, get_stage(ours, prm, "im0")) and not np.array_equal(f1, get_stage(ours, prm, "im1"))
         ref.close()
+
+
+@pytest.mark.parametrize("cfg,bbox", [("C1", None), ("small435", None), ("small", (8, 4, 64, 40)), ("C4", None)])
+def test_matrix_calibration_equals_planes(native, cfg, bbox):
+    """ss_create_calibrated: rectification maps and registration planes evaluated per pixel from 3x3 matrices (no
+    H x W plane uploaded or read) give bit-identical stages and depth to the plane-fed engine -- C1 exercises the
+    non-trivial (0.5 degree roll) remap, small435 / C4 the non-diagonal D435 registration."""
+    import math
+
+    from sapien_b200.pose import Pose
+    from sapien_b200.sensor.calibration import calibrate
+    from sapien_b200.sensor.stereodepth import StereoDepthSensorConfig
+
+    prm = configs.params(cfg)
+    model, roll, scale = {"C1": ("D415", 0.5, None), "small435": ("D435", 0.0, (128, 96, 128, 96)),
+                          "small": ("D415", 0.5, (96, 64, 144, 96)), "C4": ("D435", 0.0, (256, 256, 256, 256))}[cfg]
+    c = StereoDepthSensorConfig(model)
+    k_ir, k_rgb = c.ir_intrinsic.copy(), c.rgb_intrinsic.copy()
+    ir_size, rgb_size = c.ir_resolution, c.rgb_resolution
+    if scale is not None:  # same rescaling as oracle/configs.py
+        k_ir[0] *= scale[0] / ir_size[0]
+        k_ir[1] *= scale[1] / ir_size[1]
+        k_rgb[0] *= scale[2] / rgb_size[0]
+        k_rgb[1] *= scale[3] / rgb_size[1]
+        ir_size, rgb_size = (scale[0], scale[1]), (scale[2], scale[3])
+    pose_r = c.trans_pose_r
+    if roll:
+        a = math.radians(roll) / 2
+        pose_r = pose_r * Pose([0, 0, 0], [math.cos(a), math.sin(a), 0, 0])
+    cal = calibrate(ir_size, rgb_size, k_ir, k_rgb, c.trans_pose_l, pose_r, planes=False)
+    assert math.isclose(cal.focal_len, prm.focal_len) and math.isclose(cal.baseline_len, prm.baseline_len)
+    args = list(prm.engine_args())
+    empty = np.zeros((0,), np.float32)
+    for i in range(24, 31):  # the seven plane arguments
+        args[i] = empty
+    planes = make_engine(native, prm, keep_stages=True)
+    mats = native.DepthSensorEngine(*args, keep_stages=True, calibration=cal.matrices())
+    left, right = configs.pair(prm, seed=77)
+    bb = () if bbox is None else (True, *bbox)
+    planes.compute(left, right, *bb)
+    mats.compute(left, right, *bb)
+    for st in ("im0", "im1", "census0", "census1", "disp_wta", "disp_right", "disp_med", "depth"):
+        a, b = get_stage(mats, prm, st, bbox), get_stage(planes, prm, st, bbox)
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), st
+    assert np.array_equal(mats.get_ndarray().view(np.uint32), planes.get_ndarray().view(np.uint32))
+    # banded host output works on the matrix path too
+    import torch
+
+    out = torch.empty((prm.rgb_rows, prm.rgb_cols), dtype=torch.float32).pin_memory().numpy()
+    fast = native.DepthSensorEngine(*args, calibration=cal.matrices())
+    fast.bind_output(out)
+    fast.compute(left, right)
+    fast.get_ndarray(out=out)
+    planes.compute(left, right)
+    assert np.array_equal(out.view(np.uint32), planes.get_ndarray().view(np.uint32))
+
+
+@pytest.mark.parametrize("cfg", ["C1", "C4", "small"])
+def test_pipelined_host_frames_submit_wait(native, cfg):
+    """ss_submit_host_u8 / ss_wait_frame: two frames in flight -- uploads and front-end of frame k+1 under frame k's
+    aggregation, read-back of frame k under frame k+1.  Every delivered map must equal the same pair computed alone,
+    also when synchronous, device-input, ROI and generic-census frames are mixed into the sequence."""
+    import torch
+
+    prm = configs.params(cfg)
+    n = 7
+    pairs = [configs.pair(prm, seed=500 + i) for i in range(n)]
+    solo = make_engine(native, prm)
+    want = []
+    for l, r in pairs:
+        solo.compute(l, r)
+        want.append(solo.get_ndarray())
+    pin = [(torch.from_numpy(l).pin_memory().numpy(), torch.from_numpy(r).pin_memory().numpy()) for l, r in pairs]
+    outs = [torch.empty((prm.rgb_rows, prm.rgb_cols), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
+    eng = make_engine(native, prm)
+    for rep in range(3):
+        tickets = []
+        for i in range(n):
+            if i >= 2:  # the output buffer of frame i-2 is about to be reused: consume it first
+                eng.wait(tickets[i - 2])
+                assert np.array_equal(outs[i % 2].view(np.uint32), want[i - 2].view(np.uint32)), f"frame {i - 2} (rep {rep})"
+                outs[i % 2][:] = -5.0
+            tickets.append(eng.submit(pin[i][0], pin[i][1], out=outs[i % 2]))
+        for i in (n - 2, n - 1):
+            eng.wait(tickets[i])
+            assert np.array_equal(outs[i % 2].view(np.uint32), want[i].view(np.uint32)), f"frame {i} (rep {rep})"
+        eng.wait(tickets[0])  # waiting again for an old ticket is harmless
+    # getters after an un-waited asynchronous frame
+    t = eng.submit(pin[3][0], pin[3][1], out=outs[0])
+    assert np.array_equal(eng.get_cuda().torch().cpu().numpy().view(np.uint32), want[3].view(np.uint32))
+    assert np.array_equal(eng.get_ndarray().view(np.uint32), want[3].view(np.uint32))
+    eng.wait(t)
+    assert np.array_equal(outs[0].view(np.uint32), want[3].view(np.uint32))
+    # mixed sequence: async, sync host, device, async without host output, async ROI (no column bands), sync again
+    dl, dr = torch.from_numpy(pairs[5][0]).cuda(), torch.from_numpy(pairs[5][1]).cuda()
+    t0 = eng.submit(pin[0][0], pin[0][1], out=outs[0])
+    eng.compute(*pairs[1])
+    assert np.array_equal(eng.get_ndarray().view(np.uint32), want[1].view(np.uint32))
+    eng.wait(t0)
+    assert np.array_equal(outs[0].view(np.uint32), want[0].view(np.uint32))
+    t2 = eng.submit(pin[2][0], pin[2][1], out=outs[1])
+    eng.compute(dl, dr)
+    assert np.array_equal(eng.get_ndarray().view(np.uint32), want[5].view(np.uint32))
+    eng.wait(t2)
+    assert np.array_equal(outs[1].view(np.uint32), want[2].view(np.uint32))
+    t3 = eng.submit(pin[4][0], pin[4][1])  # no host delivery
+    eng.wait(t3)
+    assert np.array_equal(eng.get_ndarray().view(np.uint32), want[4].view(np.uint32))
+    bbox = (16, 8, prm.cols // 2, prm.rows // 2)
+    solo.compute(*pairs[6], True, *bbox)
+    roi = solo.get_ndarray()
+    t4 = eng.submit(pin[6][0], pin[6][1], outs[0], True, *bbox)
+    t5 = eng.submit(pin[0][0], pin[0][1], out=outs[1])
+    eng.wait(t4)
+    assert np.array_equal(outs[0].view(np.uint32), roi.view(np.uint32))
+    eng.wait(t5)
+    assert np.array_equal(outs[1].view(np.uint32), want[0].view(np.uint32))
+    with pytest.raises(TypeError):
+        eng.wait(10 ** 9)
+
+
+def test_pipelined_host_frames_generic_census(native):
+    """Asynchronous host frames with a census window other than 7x7 (uploads on the main stream, generic front-end)."""
+    import torch
+
+    prm = variant(configs.params("small435"), census_width=9, census_height=7)
+    pairs = [configs.pair(prm, seed=600 + i) for i in range(4)]
+    solo = make_engine(native, prm)
+    eng = make_engine(native, prm)
+    outs = [torch.empty((prm.rgb_rows, prm.rgb_cols), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
+    tickets = [None] * 4
+    for i, (l, r) in enumerate(pairs):
+        if i >= 2:
+            eng.wait(tickets[i - 2])
+            solo.compute(*pairs[i - 2])
+            assert np.array_equal(outs[i % 2].view(np.uint32), solo.get_ndarray().view(np.uint32))
+        tickets[i] = eng.submit(l, r, out=outs[i % 2])
+    for i in (2, 3):
+        eng.wait(tickets[i])
+        solo.compute(*pairs[i])
+        assert np.array_equal(outs[i % 2].view(np.uint32), solo.get_ndarray().view(np.uint32))

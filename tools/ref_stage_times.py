@@ -34,6 +34,16 @@ def main():
         ref.compute_device(dev[i % 4][0].data_ptr(), dev[i % 4][1].data_ptr(), None)
     torch.cuda.synchronize()
     sys.stdout.flush()
+    import ctypes
+
+    libc = ctypes.CDLL(None)
+    devnull = os.open(os.devnull, os.O_WRONLY)  # drop the warm-up frames' printf output
+    keep = os.dup(1)
+    os.dup2(devnull, 1)
+    libc.fflush(None)
+    os.dup2(keep, 1)
+    os.close(keep)
+    os.close(devnull)
     tmp = tempfile.NamedTemporaryFile("w+", delete=False)
     saved = os.dup(1)
     os.dup2(tmp.fileno(), 1)
@@ -42,9 +52,7 @@ def main():
         for i in range(frames):
             ref.compute_device(dev[i % 4][0].data_ptr(), dev[i % 4][1].data_ptr(), None)
         torch.cuda.synchronize()
-        import ctypes
-
-        ctypes.CDLL(None).fflush(None)
+        libc.fflush(None)
     finally:
         wall = time.perf_counter() - t0
         os.dup2(saved, 1)

@@ -28,12 +28,14 @@ dl = [torch.from_numpy(l).cuda() for l, _ in pairs]
 dr = [torch.from_numpy(r).cuda() for _, r in pairs]
 out = torch.empty((prm.rgb_rows, prm.rgb_cols), dtype=torch.float32).pin_memory().numpy()
 snaps = [torch.empty((prm.rgb_rows, prm.rgb_cols), dtype=torch.float32, device="cuda") for _ in range(n)]
+pouts = [torch.empty((prm.rgb_rows, prm.rgb_cols), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
+ppairs = [(torch.from_numpy(l).pin_memory().numpy(), torch.from_numpy(r).pin_memory().numpy()) for l, r in pairs]
 rng = np.random.default_rng(7)
 bound = False
 t0 = time.time()
 bad = 0
 for it in range(iters):
-    mode = rng.choice(["burst", "host", "bind", "unbind", "roi", "dev_sync"])
+    mode = rng.choice(["burst", "host", "bind", "unbind", "roi", "dev_sync", "pipe"])
     i = int(rng.integers(0, n))
     if mode == "burst":
         k = int(rng.integers(2, n + 1))
@@ -45,6 +47,19 @@ for it in range(iters):
         for j in range(k):
             if not np.array_equal(snaps[j].cpu().numpy().view(np.uint32), want[j].view(np.uint32)):
                 bad += 1; print("MISMATCH burst", it, j)
+    elif mode == "pipe":  # asynchronous host frames, two in flight
+        k = int(rng.integers(2, n + 1))
+        tk = []
+        for j in range(k):
+            if j >= 2:
+                eng.wait(tk[j - 2])
+                if not np.array_equal(pouts[j % 2].view(np.uint32), want[j - 2].view(np.uint32)):
+                    bad += 1; print("MISMATCH pipe", it, j - 2)
+            tk.append(eng.submit(ppairs[j][0], ppairs[j][1], out=pouts[j % 2]))
+        for j in range(max(0, k - 2), k):
+            eng.wait(tk[j])
+            if not np.array_equal(pouts[j % 2].view(np.uint32), want[j].view(np.uint32)):
+                bad += 1; print("MISMATCH pipe tail", it, j)
     elif mode == "host":
         eng.compute(*pairs[i])
         got = eng.get_ndarray(out=out) if bound else eng.get_ndarray()
