@@ -8,10 +8,6 @@ timeout 300 python tools/stress.py C4 300 > gpurun_out/${tag}_stress_c4.log 2>&1
 timeout 300 python tools/stress.py C1 120 > gpurun_out/${tag}_stress_c1.log 2>&1; tail -n 3 gpurun_out/${tag}_stress_c1.log
 timeout 600 python bench.py --steps 30 --warmup 5 > gpurun_out/${tag}_bench_c1.json 2> gpurun_out/${tag}_bench_c1.err
 tail -c 600 gpurun_out/${tag}_bench_c1.err
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/'+'TAG'+'_bench_c1.json').read().strip().splitlines()[-1]) if False else None
-PY
 python -c "
 import json,sys
 d=json.loads(open('gpurun_out/${tag}_bench_c1.json').read().strip().splitlines()[-1])
