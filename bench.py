@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batched", action="store_true", help="skip the batched block (C4 1024-env shard + C5 sweep)")
     ap.add_argument("--c4-envs", type=int, default=1024)
-    ap.add_argument("--c5-frames", type=int, default=256, help="frames of the C5 sweep over all ranks (north_star: 4096)")
+    ap.add_argument("--c5-frames", type=int, default=4096, help="frames of the C5 sweep over all ranks (north_star: 4096)")
     ap.add_argument("--pipelines", type=int, default=0, help="engines per rank for the batched block (0 = default per workload)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -337,7 +337,7 @@ def batched_ours(args, rank, world, local):
     ms5 = time_sharded(sh5, sets5, max(nb, 1), 1, torch, world) if frames else 0.0
     alg5 = configs.algorithmic_bytes(prm, rgba_input=True)
     rate5 = frames / (ms5 / 1e3) if ms5 else 0.0
-    out["C5"] = {"workload": f"C5: 1920x1080, 256 disp, sweep of {args.c5_frames} frames (north_star: 4096; --c5-frames), 4-frame batches, frames split contiguously over {world} ranks",
+    out["C5"] = {"workload": f"C5: 1920x1080, 256 disp, sweep of {args.c5_frames} frames (--c5-frames), 4-frame batches, frames split contiguously over {world} ranks",
                  "frames_per_s": rate5, "frames": frames, "frames_per_gpu": 4 * nb, "n_gpus": world, "scaling": "strong", "ms_total": ms5,
                  "pipelines_per_gpu": len(sh5.engines), "input": "device float32 RGBA [4,1080,1920,4] batches, 8 base pairs cycle",
                  "algorithmic_bytes_per_frame": int(alg5), "hbm_roofline_frames_per_s_per_gpu": peak * 1e9 / alg5,

@@ -91,6 +91,7 @@ struct ss_engine {
   cudaEvent_t ev_rawfree[2] = {nullptr, nullptr}; // front-end that read raw slot s has finished
   cudaEvent_t ev_done[2] = {nullptr, nullptr};    // host delivery of the frame in output slot s has finished
   uint64_t slot_ticket[2] = {0, 0};               // ticket (frame number + 1) whose delivery ev_done[s] stands for, 0 = none
+  bool async_unwaited = false;                    // the last frame was submitted asynchronously and nobody has waited for it yet
   bool band_pending = false;                      // the last frame's column bands (helper stream) are not yet joined into the main stream
   uint8_t *raw0s[2] = {nullptr, nullptr}, *raw1s[2] = {nullptr, nullptr};
   float *out_pair[2] = {nullptr, nullptr};        // final depth of even / odd frames (a frame's read-back overlaps the next frame)
@@ -573,6 +574,7 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
     }
   }
   if (async) e->slot_ticket[slot] = e->frame + 1;
+  e->async_unwaited = async;
   e->mark("post");
   e->launches = launches;
   e->mrows = rows; e->mcols = cols;
@@ -777,6 +779,7 @@ int ss_wait_frame(ss_engine *e, uint64_t ticket) {
     CK(cudaEventSynchronize(e->ev_done[slot]));
     e->slot_ticket[slot] = 0;
   }
+  if (ticket == e->frame) e->async_unwaited = false;
   return SS_OK;
 }
 
@@ -785,6 +788,7 @@ int ss_synchronize(ss_engine *e) {
   DeviceGuard g(e->device);
   { int r = join_async(e); if (r) return r; }
   CK(cudaStreamSynchronize(e->stream));
+  e->async_unwaited = false;
   return SS_OK;
 }
 
@@ -851,7 +855,12 @@ int ss_bind_output_host(ss_engine *e, float *out, size_t cap) {
 int ss_get_depth_device(ss_engine *e, void **ptr) {
   if (!e || !ptr) return fail(SS_ERR_INVALID, "null argument");
   if (!e->computed) return fail(SS_ERR_NOT_COMPUTED, "No computed data stored");
-  if (e->band_pending) { DeviceGuard g(e->device); int r = join_async(e); if (r) return r; }
+  if (e->band_pending || e->async_unwaited) { // an asynchronous host frame nobody waited for: the getter waits (its caller
+    DeviceGuard g(e->device);                  // has no stream the result could be ordered on)
+    int r = join_async(e); if (r) return r;
+    CK(cudaStreamSynchronize(e->stream));
+    e->async_unwaited = false;
+  }
   *ptr = e->out;
   return SS_OK;
 }
