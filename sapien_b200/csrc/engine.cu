@@ -78,7 +78,7 @@ int validate_params(const ss_config &c) {
 
 } // namespace
 
-struct ss_engine {
+struct Core {
   ss_config cfg{};
   int device = 0;
   cudaStream_t stream = nullptr, aux = nullptr, cpy = nullptr;
@@ -168,14 +168,14 @@ struct ss_engine {
 
 namespace {
 
-int upload(ss_engine *e, float **dst, const float *src, size_t n) {
+int upload(Core *e, float **dst, const float *src, size_t n) {
   int r = e->alloc(dst, n);
   if (r) return r;
   CK(cudaMemcpyAsync(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
   return SS_OK;
 }
 
-int create_impl(ss_engine *e, const float *mapLx, const float *mapLy, const float *mapRx,
+int create_impl(Core *e, const float *mapLx, const float *mapLy, const float *mapRx,
                 const float *mapRy, const float *a1, const float *a2, const float *a3) {
   const ss_config &c = e->cfg;
   std::vector<float> ha1, ha3; // matrix calibration: host copies of a1 / a3, only for the banded-output bound below
@@ -301,7 +301,7 @@ enum InputKind { IN_U8, IN_RGBA };
 // inputs_on_main: left/right are engine-owned buffers whose uploads were enqueued on the main stream
 // async_out: asynchronous host frame (ss_submit_host_u8): this frame's depth map goes to *async_out (may be null for
 // "no host delivery") and the main stream is NOT made to wait for the delivery -- ev_done[frame & 1] stands for it
-int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *right,
+int compute_impl(Core *e, InputKind kind, const void *left, const void *right,
                  const ss_bbox *bbox, cudaStream_t user, const uint8_t *host_left = nullptr,
                  const uint8_t *host_right = nullptr, bool inputs_on_main = false,
                  size_t env_pitch = 0, size_t row_pitch = 0, // pitches in source elements, 0 = packed
@@ -356,7 +356,7 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
   const size_t fsz = e->fsz(), msz = (size_t)rows * cols;
   int launches = 0;
   // Banded output plan (see ss_bind_output_host): up to 4 progress points of the final pass -> up to 5 bands
-  int nseg = 0, seg_end[ss_engine::MAXSEG];
+  int nseg = 0, seg_end[Core::MAXSEG];
   bool banded = false;
   // Host-input frames have a host consumer: without a bound buffer they stream into the engine's own pinned
   // staging buffer and ss_get_depth_host copies from there (a pageable 8.3 MB cudaMemcpy costs ~2 ms at C1).
@@ -372,7 +372,7 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
     }
     if (nseg > 0) {
       banded = true; // (the last band, up to cols, follows the end of the kernel)
-      if (!e->progress) { int r = e->alloc(&e->progress, ss_engine::MAXSEG); if (r) return r; }
+      if (!e->progress) { int r = e->alloc(&e->progress, Core::MAXSEG); if (r) return r; }
     }
   }
   for (int w0 = 0; w0 < c.batch; w0 += e->wave) {
@@ -466,7 +466,7 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
     ab.dispL = e->dispL + (size_t)w0 * msz; ab.dispR = e->dispR + (size_t)w0 * msz;
     if (fast) {
       if (!c.keep_stages) { ab.dbgL0 = ab.dbgL3 = ab.dbgLAll = nullptr; }
-      AggrMarks am{[](void *ctx, const char *name) { static_cast<ss_engine *>(ctx)->mark(name); }, e};
+      AggrMarks am{[](void *ctx, const char *name) { static_cast<Core *>(ctx)->mark(name); }, e};
       CK(launch_aggr_passes(ab, wn, rows, cols, D, P1, P2, c.uniq_ratio, st, e->aux, e->ev, e->profiling ? &am : nullptr));
       launches += 3;
       if (!banded) { // (banded: the final pass follows below, with its progress counters)
@@ -516,7 +516,7 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
     const size_t pitch = (size_t)ocols * sizeof(float);
     { int r = join_prev_bands(); if (r) return r; } // (also: nobody polls the progress counters any more)
     CK(cudaStreamWaitEvent(e->aux, e->ev_done[slot], 0)); // the read-back of the frame that last used this output slot
-    CK(cudaMemsetAsync(e->progress, 0, ss_engine::MAXSEG * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(e->progress, 0, Core::MAXSEG * sizeof(uint32_t), st));
     CK(cudaEventRecord(e->ev_seg[0], st));
     CK(cudaStreamWaitEvent(e->aux, e->ev_seg[0], 0)); // counters are zero before anybody waits on them
     CK(launch_aggr_final(ab, c.batch, rows, cols, D, P1, P2, c.uniq_ratio, st, e->progress, nseg, seg_end));
@@ -591,7 +591,7 @@ int compute_impl(ss_engine *e, InputKind kind, const void *left, const void *rig
 
 // Host-facing calls that read results through the main stream first join whatever an asynchronous frame left on the
 // helper and copy streams (its column bands and their copies).
-static int join_async(ss_engine *e) {
+static int join_async(Core *e) {
   if (e->band_pending) {
     CK(cudaStreamWaitEvent(e->stream, e->ev_lastband[e->band_slot], 0));
     CK(cudaStreamWaitEvent(e->stream, e->ev_done[e->band_slot], 0));
@@ -600,22 +600,20 @@ static int join_async(ss_engine *e) {
   return SS_OK;
 }
 
-extern "C" {
-
-const char *ss_last_error(void) { return g_err.c_str(); }
-const char *ss_version(void) { return "ss_b200 0.1 (sm_100a)"; }
+// ---- one lane: the C-ABI operations on a single Core (the public entry points are at the end of the file) ----
 
 static int create_common(const ss_config *cfg, const ss_calibration *cal, const float *mapLx, const float *mapLy,
                          const float *mapRx, const float *mapRy, const float *a1, const float *a2, const float *a3,
-                         ss_engine **out);
+                         Core **out);
+static int core_destroy(Core *e);
 
-int ss_create(const ss_config *cfg, const float *mapLx, const float *mapLy, const float *mapRx,
+static int core_create(const ss_config *cfg, const float *mapLx, const float *mapLy, const float *mapRx,
               const float *mapRy, const float *a1, const float *a2, const float *a3,
-              ss_engine **out) {
+              Core **out) {
   return create_common(cfg, nullptr, mapLx, mapLy, mapRx, mapRy, a1, a2, a3, out);
 }
 
-int ss_create_calibrated(const ss_config *cfg, const ss_calibration *cal, ss_engine **out) {
+static int core_create_calibrated(const ss_config *cfg, const ss_calibration *cal, Core **out) {
   if (!cal) return fail(SS_ERR_INVALID, "null calibration");
   for (double v : cal->reg_m) if (!std::isfinite(v)) return fail(SS_ERR_INVALID, "registration matrix is not finite");
   if (cfg && !cfg->rectified) {
@@ -628,7 +626,7 @@ int ss_create_calibrated(const ss_config *cfg, const ss_calibration *cal, ss_eng
 
 static int create_common(const ss_config *cfg, const ss_calibration *cal, const float *mapLx, const float *mapLy,
                          const float *mapRx, const float *mapRy, const float *a1, const float *a2, const float *a3,
-                         ss_engine **out) {
+                         Core **out) {
   if (!cfg || !out) return fail(SS_ERR_INVALID, "null argument");
   *out = nullptr;
   int r = validate_params(*cfg);
@@ -646,19 +644,19 @@ static int create_common(const ss_config *cfg, const ss_calibration *cal, const 
   if (prop.major != 10) return fail(SS_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100: this build targets B200 only");
   DeviceGuard g(dev);
   if (!g.ok) return fail(SS_ERR_CUDA, "cudaSetDevice failed");
-  ss_engine *e = new ss_engine();
+  Core *e = new Core();
   e->cfg = *cfg;
   if (e->cfg.lr_max_diff == -1) e->cfg.lr_max_diff = 255; // uint8_t wrap in the reference ctor
   e->device = dev;
   e->cfg.device = dev;
   if (cal) { e->has_cal = true; e->cal = *cal; }
   r = create_impl(e, mapLx, mapLy, mapRx, mapRy, a1, a2, a3);
-  if (r) { std::string keep = g_err; ss_destroy(e); g_err = keep; return r; }
+  if (r) { std::string keep = g_err; core_destroy(e); g_err = keep; return r; }
   *out = e;
   return SS_OK;
 }
 
-int ss_destroy(ss_engine *e) {
+static int core_destroy(Core *e) {
   if (!e) return SS_OK;
   DeviceGuard g(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
@@ -687,7 +685,7 @@ int ss_destroy(ss_engine *e) {
   return SS_OK;
 }
 
-int ss_compute_host_u8(ss_engine *e, const uint8_t *left, const uint8_t *right, const ss_bbox *bbox) {
+static int core_compute_host_u8(Core *e, const uint8_t *left, const uint8_t *right, const ss_bbox *bbox) {
   if (!e || !left || !right) return fail(SS_ERR_INVALID, "null argument");
   DeviceGuard g(e->device);
   const size_t bytes = (size_t)e->cfg.batch * e->fsz();
@@ -707,13 +705,13 @@ int ss_compute_host_u8(ss_engine *e, const uint8_t *left, const uint8_t *right, 
   return SS_OK;
 }
 
-int ss_compute_device_rgba_f32(ss_engine *e, const void *left, const void *right, const ss_bbox *bbox, void *stream) {
+static int core_compute_device_rgba_f32(Core *e, const void *left, const void *right, const ss_bbox *bbox, void *stream) {
   if (!e) return fail(SS_ERR_INVALID, "null engine");
   DeviceGuard g(e->device);
   return compute_impl(e, IN_RGBA, left, right, bbox, static_cast<cudaStream_t>(stream));
 }
 
-int ss_compute_device_rgba_f32_pitched(ss_engine *e, const void *left, const void *right, size_t env_pitch_bytes,
+static int core_compute_device_rgba_f32_pitched(Core *e, const void *left, const void *right, size_t env_pitch_bytes,
                                        size_t row_pitch_bytes, const ss_bbox *bbox, void *stream) {
   if (!e) return fail(SS_ERR_INVALID, "null engine");
   const size_t row_min = (size_t)e->cfg.cols * 16;
@@ -729,13 +727,13 @@ int ss_compute_device_rgba_f32_pitched(ss_engine *e, const void *left, const voi
                       env_pitch_bytes / 4, row_pitch_bytes / 4);
 }
 
-int ss_compute_device_u8(ss_engine *e, const void *left, const void *right, const ss_bbox *bbox, void *stream) {
+static int core_compute_device_u8(Core *e, const void *left, const void *right, const ss_bbox *bbox, void *stream) {
   if (!e) return fail(SS_ERR_INVALID, "null engine");
   DeviceGuard g(e->device);
   return compute_impl(e, IN_U8, left, right, bbox, static_cast<cudaStream_t>(stream));
 }
 
-int ss_wait_stream(ss_engine *e, void *stream) {
+static int core_wait_stream(Core *e, void *stream) {
   if (!e) return fail(SS_ERR_INVALID, "null engine");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!s || s == e->stream) return SS_OK;
@@ -747,7 +745,7 @@ int ss_wait_stream(ss_engine *e, void *stream) {
   return SS_OK;
 }
 
-int ss_submit_host_u8(ss_engine *e, const uint8_t *left, const uint8_t *right, const ss_bbox *bbox, float *out_host,
+static int core_submit_host_u8(Core *e, const uint8_t *left, const uint8_t *right, const ss_bbox *bbox, float *out_host,
                       size_t capacity_bytes, uint64_t *ticket) {
   if (!e || !left || !right || !ticket) return fail(SS_ERR_INVALID, "null argument");
   if (out_host && capacity_bytes < (size_t)e->cfg.batch * e->rsz() * sizeof(float)) return fail(SS_ERR_INVALID, "output buffer too small");
@@ -770,7 +768,7 @@ int ss_submit_host_u8(ss_engine *e, const uint8_t *left, const uint8_t *right, c
   return SS_OK;
 }
 
-int ss_wait_frame(ss_engine *e, uint64_t ticket) {
+static int core_wait_frame(Core *e, uint64_t ticket) {
   if (!e) return fail(SS_ERR_INVALID, "null engine");
   if (ticket == 0 || ticket > e->frame) return fail(SS_ERR_INVALID, "unknown frame ticket");
   DeviceGuard g(e->device);
@@ -783,7 +781,7 @@ int ss_wait_frame(ss_engine *e, uint64_t ticket) {
   return SS_OK;
 }
 
-int ss_synchronize(ss_engine *e) {
+static int core_synchronize(Core *e) {
   if (!e) return fail(SS_ERR_INVALID, "null engine");
   DeviceGuard g(e->device);
   { int r = join_async(e); if (r) return r; }
@@ -792,28 +790,28 @@ int ss_synchronize(ss_engine *e) {
   return SS_OK;
 }
 
-int ss_get_output_shape(const ss_engine *e, uint32_t *rows, uint32_t *cols) {
+static int core_get_output_shape(const Core *e, uint32_t *rows, uint32_t *cols) {
   if (!e || !rows || !cols) return fail(SS_ERR_INVALID, "null argument");
   *rows = e->out_rows(); *cols = e->out_cols();
   return SS_OK;
 }
-int ss_get_input_shape(const ss_engine *e, uint32_t *rows, uint32_t *cols) {
+static int core_get_input_shape(const Core *e, uint32_t *rows, uint32_t *cols) {
   if (!e || !rows || !cols) return fail(SS_ERR_INVALID, "null argument");
   *rows = e->cfg.rows; *cols = e->cfg.cols;
   return SS_OK;
 }
-int ss_get_stream(const ss_engine *e, void **stream) {
+static int core_get_stream(const Core *e, void **stream) {
   if (!e || !stream) return fail(SS_ERR_INVALID, "null argument");
   *stream = e->stream;
   return SS_OK;
 }
-int ss_get_device(const ss_engine *e, int32_t *device) {
+static int core_get_device(const Core *e, int32_t *device) {
   if (!e || !device) return fail(SS_ERR_INVALID, "null argument");
   *device = e->device;
   return SS_OK;
 }
 
-static int copy_out(ss_engine *e, const float *src, size_t count, float *out, size_t cap) {
+static int copy_out(Core *e, const float *src, size_t count, float *out, size_t cap) {
   if (!out) return fail(SS_ERR_INVALID, "null output");
   if (cap < count * sizeof(float)) return fail(SS_ERR_INVALID, "output buffer too small");
   CK(cudaMemcpyAsync(out, src, count * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
@@ -821,7 +819,7 @@ static int copy_out(ss_engine *e, const float *src, size_t count, float *out, si
   return SS_OK;
 }
 
-int ss_get_depth_host(ss_engine *e, float *out, size_t cap) {
+static int core_get_depth_host(Core *e, float *out, size_t cap) {
   if (!e) return fail(SS_ERR_INVALID, "null engine");
   if (!e->computed) return fail(SS_ERR_NOT_COMPUTED, "No computed data stored");
   DeviceGuard g(e->device);
@@ -840,7 +838,7 @@ int ss_get_depth_host(ss_engine *e, float *out, size_t cap) {
   return copy_out(e, e->out, (size_t)e->cfg.batch * e->rsz(), out, cap);
 }
 
-int ss_bind_output_host(ss_engine *e, float *out, size_t cap) {
+static int core_bind_output_host(Core *e, float *out, size_t cap) {
   if (!e) return fail(SS_ERR_INVALID, "null engine");
   if (out && cap < (size_t)e->cfg.batch * e->rsz() * sizeof(float)) return fail(SS_ERR_INVALID, "output buffer too small");
   DeviceGuard g(e->device);
@@ -852,7 +850,7 @@ int ss_bind_output_host(ss_engine *e, float *out, size_t cap) {
   e->stream_dst = nullptr;
   return SS_OK;
 }
-int ss_get_depth_device(ss_engine *e, void **ptr) {
+static int core_get_depth_device(Core *e, void **ptr) {
   if (!e || !ptr) return fail(SS_ERR_INVALID, "null argument");
   if (!e->computed) return fail(SS_ERR_NOT_COMPUTED, "No computed data stored");
   if (e->band_pending || e->async_unwaited) { // an asynchronous host frame nobody waited for: the getter waits (its caller
@@ -864,7 +862,7 @@ int ss_get_depth_device(ss_engine *e, void **ptr) {
   *ptr = e->out;
   return SS_OK;
 }
-static int run_pc(ss_engine *e, const void *rgba) {
+static int run_pc(Core *e, const void *rgba) {
   const ss_config &c = e->cfg;
   { int r = join_async(e); if (r) return r; }
   if (rgba) { // the colour image may still be in flight on the caller's (default) stream
@@ -876,7 +874,7 @@ static int run_pc(ss_engine *e, const void *rgba) {
                         c.main_cx, c.main_cy, e->stream));
   return SS_OK;
 }
-int ss_get_point_cloud_host(ss_engine *e, float *out, size_t cap) {
+static int core_get_point_cloud_host(Core *e, float *out, size_t cap) {
   if (!e) return fail(SS_ERR_INVALID, "null engine");
   if (!e->computed) return fail(SS_ERR_NOT_COMPUTED, "No computed data stored");
   DeviceGuard g(e->device);
@@ -884,7 +882,7 @@ int ss_get_point_cloud_host(ss_engine *e, float *out, size_t cap) {
   if (r) return r;
   return copy_out(e, e->pc, (size_t)e->cfg.batch * e->rsz() * 3, out, cap);
 }
-int ss_get_point_cloud_device(ss_engine *e, void **ptr) {
+static int core_get_point_cloud_device(Core *e, void **ptr) {
   if (!e || !ptr) return fail(SS_ERR_INVALID, "null argument");
   if (!e->computed) return fail(SS_ERR_NOT_COMPUTED, "No computed data stored");
   DeviceGuard g(e->device);
@@ -894,7 +892,7 @@ int ss_get_point_cloud_device(ss_engine *e, void **ptr) {
   *ptr = e->pc;
   return SS_OK;
 }
-int ss_get_rgb_point_cloud_host(ss_engine *e, const void *rgba, float *out, size_t cap) {
+static int core_get_rgb_point_cloud_host(Core *e, const void *rgba, float *out, size_t cap) {
   if (!e || !rgba) return fail(SS_ERR_INVALID, "null argument");
   if (!e->computed) return fail(SS_ERR_NOT_COMPUTED, "No computed data stored");
   DeviceGuard g(e->device);
@@ -902,7 +900,7 @@ int ss_get_rgb_point_cloud_host(ss_engine *e, const void *rgba, float *out, size
   if (r) return r;
   return copy_out(e, e->rgbpc, (size_t)e->cfg.batch * e->rsz() * 6, out, cap);
 }
-int ss_get_rgb_point_cloud_device(ss_engine *e, const void *rgba, void **ptr) {
+static int core_get_rgb_point_cloud_device(Core *e, const void *rgba, void **ptr) {
   if (!e || !rgba || !ptr) return fail(SS_ERR_INVALID, "null argument");
   if (!e->computed) return fail(SS_ERR_NOT_COMPUTED, "No computed data stored");
   DeviceGuard g(e->device);
@@ -913,7 +911,7 @@ int ss_get_rgb_point_cloud_device(ss_engine *e, const void *rgba, void **ptr) {
   return SS_OK;
 }
 
-int ss_set_ir_noise_parameters(ss_engine *e, float shape, float scale, float mu, float sigma) {
+static int core_set_ir_noise_parameters(Core *e, float shape, float scale, float mu, float sigma) {
   if (!e) return fail(SS_ERR_INVALID, "null engine");
   e->cfg.speckle_shape = shape; e->cfg.speckle_scale = scale;
   e->cfg.gaussian_mu = mu; e->cfg.gaussian_sigma = sigma;
@@ -927,13 +925,13 @@ int ss_set_ir_noise_parameters(ss_engine *e, float shape, float scale, float mu,
   if (r) return r;                                                                                \
   e->cfg = t;                                                                                     \
   return SS_OK;
-int ss_set_penalties(ss_engine *e, int32_t p1, int32_t p2) { SET_VALIDATED(t.p1 = p1; t.p2 = p2) }
-int ss_set_census_window_size(ss_engine *e, int32_t w, int32_t h) { SET_VALIDATED(t.census_width = w; t.census_height = h) }
-int ss_set_matching_block_size(ss_engine *e, int32_t w, int32_t h) { SET_VALIDATED(t.bf_width = w; t.bf_height = h) }
-int ss_set_uniqueness_ratio(ss_engine *e, int32_t u) { SET_VALIDATED(t.uniq_ratio = u) }
-int ss_set_lr_max_diff(ss_engine *e, int32_t d) { SET_VALIDATED(t.lr_max_diff = (d == -1 ? 255 : d)) }
+static int core_set_penalties(Core *e, int32_t p1, int32_t p2) { SET_VALIDATED(t.p1 = p1; t.p2 = p2) }
+static int core_set_census_window_size(Core *e, int32_t w, int32_t h) { SET_VALIDATED(t.census_width = w; t.census_height = h) }
+static int core_set_matching_block_size(Core *e, int32_t w, int32_t h) { SET_VALIDATED(t.bf_width = w; t.bf_height = h) }
+static int core_set_uniqueness_ratio(Core *e, int32_t u) { SET_VALIDATED(t.uniq_ratio = u) }
+static int core_set_lr_max_diff(Core *e, int32_t d) { SET_VALIDATED(t.lr_max_diff = (d == -1 ? 255 : d)) }
 
-int ss_get_stage_host(ss_engine *e, const char *name, int32_t index, void *out, size_t cap, size_t *bytes) {
+static int core_get_stage_host(Core *e, const char *name, int32_t index, void *out, size_t cap, size_t *bytes) {
   if (!e || !name || !out) return fail(SS_ERR_INVALID, "null argument");
   if (!e->computed) return fail(SS_ERR_NOT_COMPUTED, "No computed data stored");
   if (index < 0 || index >= e->cfg.batch) return fail(SS_ERR_INVALID, "batch index out of range");
@@ -976,21 +974,12 @@ int ss_get_stage_host(ss_engine *e, const char *name, int32_t index, void *out, 
   return SS_OK;
 }
 
-int ss_pointer_device(const void *ptr, int32_t *device) {
-  if (!device) return fail(SS_ERR_INVALID, "null argument");
-  cudaPointerAttributes attr{};
-  cudaError_t err = cudaPointerGetAttributes(&attr, ptr);
-  if (err != cudaSuccess) { cudaGetLastError(); *device = -1; return fail(SS_ERR_CUDA, cudaGetErrorString(err)); }
-  *device = (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) ? attr.device : -1;
-  return SS_OK;
-}
-
-int ss_set_profiling(ss_engine *e, int32_t enabled) {
+static int core_set_profiling(Core *e, int32_t enabled) {
   if (!e) return fail(SS_ERR_INVALID, "null engine");
   e->profiling = enabled != 0;
   return SS_OK;
 }
-int ss_get_stage_times(ss_engine *e, const char **names, float *ms, int32_t capacity, int32_t *count,
+static int core_get_stage_times(Core *e, const char **names, float *ms, int32_t capacity, int32_t *count,
                        int32_t *frames) {
   if (!e || !count) return fail(SS_ERR_INVALID, "null argument");
   DeviceGuard g(e->device);
@@ -1017,10 +1006,225 @@ int ss_get_stage_times(ss_engine *e, const char **names, float *ms, int32_t capa
   e->pev.clear(); e->pnames.clear();
   return SS_OK;
 }
-int ss_get_launches_per_compute(ss_engine *e, int32_t *count) {
+static int core_get_launches_per_compute(Core *e, int32_t *count) {
   if (!e || !count) return fail(SS_ERR_INVALID, "null argument");
   *count = e->launches;
   return SS_OK;
+}
+
+// =====================================================================================================================
+// The public engine: one or two LANES behind the C ABI.
+//
+// A lane (Core) owns a complete set of streams and buffers.  Single frames of one stereo pair leave every kernel with
+// a latency-bound head and tail (a 720-row pass cannot fill 148 SMs evenly; the final pass is a serial chain per row),
+// and kernels of one stream run back to back, so with ONE lane those phases add up.  With two lanes consecutive
+// frames alternate between two independent stream sets and the tail of one frame's kernel is filled by the other
+// frame's kernels: C1 1 954 -> 2 252 frames/s with device inputs (tools/pipe_experiment.py, round 2), bit-identical
+// results.  Batched engines (many environments per call) already fill the machine and gain nothing: they get one lane.
+//
+// The engine's PUBLIC stream (ss_get_stream) runs no kernels: it waits, in submission order, for the end of every
+// frame, so work enqueued on it after compute() sees that frame (and all earlier ones).  A frame starts only after the
+// work that was on the public stream when the PREVIOUS frame was enqueued -- i.e. after every consumer of the frame that
+// last used its lane -- which keeps "borrowed result pointer + stream order" safe without serialising the lanes.
+// =====================================================================================================================
+struct ss_engine {
+  Core *lane[2] = {nullptr, nullptr};
+  int nlanes = 1;
+  int last = 0;          // lane of the most recent frame
+  uint64_t frames = 0;   // frames enqueued so far
+  int device = 0;
+  bool profiling = false; // stage times are measured with the frames of ONE lane running alone
+  cudaStream_t pub = nullptr;
+  cudaEvent_t ev_join = nullptr, ev_tail[2] = {nullptr, nullptr};
+  struct Ticket { uint64_t pub = 0, sub = 0; int lane = 0; } tk[4];
+
+  int next_lane() const { return (profiling || nlanes == 1) ? 0 : (int)(frames % (uint64_t)nlanes); }
+};
+
+namespace {
+
+// before a frame is enqueued on `lane`: order it after the public stream as it was when the previous frame was enqueued
+int lane_begin(ss_engine *e, int lane) {
+  if (e->frames > 0) CK(cudaStreamWaitEvent(e->lane[lane]->stream, e->ev_tail[(e->frames - 1) & 1], 0));
+  return SS_OK;
+}
+// after a frame has been enqueued on `lane`: the public stream completes behind it
+int lane_end(ss_engine *e, int lane) {
+  CK(cudaEventRecord(e->ev_tail[e->frames & 1], e->pub)); // (the public stream BEFORE this frame's join)
+  CK(cudaEventRecord(e->ev_join, e->lane[lane]->stream));
+  CK(cudaStreamWaitEvent(e->pub, e->ev_join, 0));
+  e->last = lane;
+  e->frames++;
+  return SS_OK;
+}
+// caller streams: the public stream itself (or null) means "the inputs are complete, no ordering"
+void *user_stream(const ss_engine *e, void *stream) { return stream == (void *)e->pub ? nullptr : stream; }
+
+int create_lanes(const ss_config *cfg, const ss_calibration *cal, const float *mapLx, const float *mapLy, const float *mapRx,
+                 const float *mapRy, const float *a1, const float *a2, const float *a3, ss_engine **out) {
+  if (!cfg || !out) return fail(SS_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->lanes < 0 || cfg->lanes > 2) return fail(SS_ERR_INVALID, "lanes must be 0 (automatic), 1 or 2");
+  ss_engine *e = new ss_engine();
+  auto make = [&](Core **c) {
+    return cal ? core_create_calibrated(cfg, cal, c) : core_create(cfg, mapLx, mapLy, mapRx, mapRy, a1, a2, a3, c);
+  };
+  int r = make(&e->lane[0]);
+  if (r) { delete e; return r; }
+  e->device = e->lane[0]->device;
+  const int want = cfg->lanes ? cfg->lanes : ((cfg->batch == 1 && !cfg->keep_stages) ? 2 : 1);
+  if (want == 2) {
+    ss_config c2 = *cfg;
+    c2.device = e->device;
+    const ss_config *saved = cfg;
+    cfg = &c2;
+    const std::string keep = g_err;
+    if (make(&e->lane[1]) == SS_OK) e->nlanes = 2; // (no memory for a second lane: one lane, silently)
+    else { e->lane[1] = nullptr; g_err = keep; cudaGetLastError(); }
+    cfg = saved;
+  }
+  DeviceGuard g(e->device);
+  cudaError_t ce = cudaStreamCreateWithFlags(&e->pub, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming);
+  for (auto &ev : e->ev_tail) if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  if (ce != cudaSuccess) { ss_destroy(e); return fail(SS_ERR_CUDA, cudaGetErrorString(ce)); }
+  *out = e;
+  return SS_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *ss_last_error(void) { return g_err.c_str(); }
+const char *ss_version(void) { return "ss_b200 0.2 (sm_100a)"; }
+
+int ss_pointer_device(const void *ptr, int32_t *device) {
+  if (!device) return fail(SS_ERR_INVALID, "null argument");
+  cudaPointerAttributes attr{};
+  cudaError_t err = cudaPointerGetAttributes(&attr, ptr);
+  if (err != cudaSuccess) { cudaGetLastError(); *device = -1; return fail(SS_ERR_CUDA, cudaGetErrorString(err)); }
+  *device = (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) ? attr.device : -1;
+  return SS_OK;
+}
+
+int ss_create(const ss_config *cfg, const float *mapLx, const float *mapLy, const float *mapRx, const float *mapRy,
+              const float *a1, const float *a2, const float *a3, ss_engine **out) {
+  return create_lanes(cfg, nullptr, mapLx, mapLy, mapRx, mapRy, a1, a2, a3, out);
+}
+int ss_create_calibrated(const ss_config *cfg, const ss_calibration *cal, ss_engine **out) {
+  if (!cal) return fail(SS_ERR_INVALID, "null calibration");
+  return create_lanes(cfg, cal, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, out);
+}
+int ss_destroy(ss_engine *e) {
+  if (!e) return SS_OK;
+  for (Core *c : e->lane) core_destroy(c);
+  DeviceGuard g(e->device);
+  if (e->pub) { cudaStreamSynchronize(e->pub); cudaStreamDestroy(e->pub); }
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
+  for (auto ev : e->ev_tail) if (ev) cudaEventDestroy(ev);
+  delete e;
+  return SS_OK;
+}
+
+#define SS_FRAME(call)                                                                                                 \
+  if (!e) return fail(SS_ERR_INVALID, "null engine");                                                                  \
+  DeviceGuard g(e->device);                                                                                            \
+  const int ln = e->next_lane();                                                                                       \
+  Core *c = e->lane[ln];                                                                                               \
+  int r = lane_begin(e, ln);                                                                                           \
+  if (r) return r;                                                                                                     \
+  r = (call);                                                                                                          \
+  if (r) return r;                                                                                                     \
+  return lane_end(e, ln);
+
+int ss_compute_host_u8(ss_engine *e, const uint8_t *left, const uint8_t *right, const ss_bbox *bbox) {
+  SS_FRAME(core_compute_host_u8(c, left, right, bbox))
+}
+int ss_compute_device_rgba_f32(ss_engine *e, const void *left, const void *right, const ss_bbox *bbox, void *stream) {
+  SS_FRAME(core_compute_device_rgba_f32(c, left, right, bbox, user_stream(e, stream)))
+}
+int ss_compute_device_rgba_f32_pitched(ss_engine *e, const void *left, const void *right, size_t env_pitch_bytes,
+                                       size_t row_pitch_bytes, const ss_bbox *bbox, void *stream) {
+  SS_FRAME(core_compute_device_rgba_f32_pitched(c, left, right, env_pitch_bytes, row_pitch_bytes, bbox, user_stream(e, stream)))
+}
+int ss_compute_device_u8(ss_engine *e, const void *left, const void *right, const ss_bbox *bbox, void *stream) {
+  SS_FRAME(core_compute_device_u8(c, left, right, bbox, user_stream(e, stream)))
+}
+int ss_submit_host_u8(ss_engine *e, const uint8_t *left, const uint8_t *right, const ss_bbox *bbox, float *out_host,
+                      size_t capacity_bytes, uint64_t *ticket) {
+  if (!ticket) return fail(SS_ERR_INVALID, "null argument");
+  uint64_t sub = 0;
+  const uint64_t mine = e ? e->frames + 1 : 0;
+  SS_FRAME((r = core_submit_host_u8(c, left, right, bbox, out_host, capacity_bytes, &sub),
+            r ? r : (e->tk[mine & 3] = {mine, sub, ln}, *ticket = mine, 0)))
+}
+int ss_wait_frame(ss_engine *e, uint64_t ticket) {
+  if (!e) return fail(SS_ERR_INVALID, "null engine");
+  if (ticket == 0 || ticket > e->frames) return fail(SS_ERR_INVALID, "unknown frame ticket");
+  const ss_engine::Ticket &t = e->tk[ticket & 3];
+  if (t.pub != ticket) return SS_OK; // an old ticket: the lanes' in-flight limit has already waited for that frame
+  return core_wait_frame(e->lane[t.lane], t.sub);
+}
+int ss_wait_stream(ss_engine *e, void *stream) {
+  if (!e) return fail(SS_ERR_INVALID, "null engine");
+  if (stream == (void *)e->pub) return SS_OK;
+  return core_wait_stream(e->lane[e->next_lane()], stream);
+}
+int ss_synchronize(ss_engine *e) {
+  if (!e) return fail(SS_ERR_INVALID, "null engine");
+  for (int i = 0; i < e->nlanes; ++i) { int r = core_synchronize(e->lane[i]); if (r) return r; }
+  DeviceGuard g(e->device);
+  CK(cudaStreamSynchronize(e->pub));
+  return SS_OK;
+}
+
+int ss_get_output_shape(const ss_engine *e, uint32_t *rows, uint32_t *cols) { return e ? core_get_output_shape(e->lane[0], rows, cols) : fail(SS_ERR_INVALID, "null argument"); }
+int ss_get_input_shape(const ss_engine *e, uint32_t *rows, uint32_t *cols) { return e ? core_get_input_shape(e->lane[0], rows, cols) : fail(SS_ERR_INVALID, "null argument"); }
+int ss_get_device(const ss_engine *e, int32_t *device) { return e ? core_get_device(e->lane[0], device) : fail(SS_ERR_INVALID, "null argument"); }
+int ss_get_stream(const ss_engine *e, void **stream) {
+  if (!e || !stream) return fail(SS_ERR_INVALID, "null argument");
+  *stream = e->pub;
+  return SS_OK;
+}
+int ss_get_lanes(const ss_engine *e, int32_t *lanes) {
+  if (!e || !lanes) return fail(SS_ERR_INVALID, "null argument");
+  *lanes = e->nlanes;
+  return SS_OK;
+}
+
+#define SS_LAST(fn, ...) return e ? fn(e->lane[e->last], ##__VA_ARGS__) : fail(SS_ERR_INVALID, "null engine");
+int ss_get_depth_host(ss_engine *e, float *out, size_t cap) { SS_LAST(core_get_depth_host, out, cap) }
+int ss_get_depth_device(ss_engine *e, void **ptr) { SS_LAST(core_get_depth_device, ptr) }
+int ss_get_point_cloud_host(ss_engine *e, float *out, size_t cap) { SS_LAST(core_get_point_cloud_host, out, cap) }
+int ss_get_point_cloud_device(ss_engine *e, void **ptr) { SS_LAST(core_get_point_cloud_device, ptr) }
+int ss_get_rgb_point_cloud_host(ss_engine *e, const void *rgba, float *out, size_t cap) { SS_LAST(core_get_rgb_point_cloud_host, rgba, out, cap) }
+int ss_get_rgb_point_cloud_device(ss_engine *e, const void *rgba, void **ptr) { SS_LAST(core_get_rgb_point_cloud_device, rgba, ptr) }
+int ss_get_stage_host(ss_engine *e, const char *name, int32_t index, void *out, size_t cap, size_t *bytes) {
+  SS_LAST(core_get_stage_host, name, index, out, cap, bytes)
+}
+int ss_get_launches_per_compute(ss_engine *e, int32_t *count) { SS_LAST(core_get_launches_per_compute, count) }
+
+#define SS_ALL(fn, ...)                                                                                                \
+  if (!e) return fail(SS_ERR_INVALID, "null engine");                                                                  \
+  for (int i = 0; i < e->nlanes; ++i) { int r = fn(e->lane[i], ##__VA_ARGS__); if (r) return r; }                       \
+  return SS_OK;
+int ss_bind_output_host(ss_engine *e, float *out, size_t cap) { SS_ALL(core_bind_output_host, out, cap) }
+int ss_set_ir_noise_parameters(ss_engine *e, float shape, float scale, float mu, float sigma) { SS_ALL(core_set_ir_noise_parameters, shape, scale, mu, sigma) }
+int ss_set_penalties(ss_engine *e, int32_t p1, int32_t p2) { SS_ALL(core_set_penalties, p1, p2) }
+int ss_set_census_window_size(ss_engine *e, int32_t w, int32_t h) { SS_ALL(core_set_census_window_size, w, h) }
+int ss_set_matching_block_size(ss_engine *e, int32_t w, int32_t h) { SS_ALL(core_set_matching_block_size, w, h) }
+int ss_set_uniqueness_ratio(ss_engine *e, int32_t u) { SS_ALL(core_set_uniqueness_ratio, u) }
+int ss_set_lr_max_diff(ss_engine *e, int32_t d) { SS_ALL(core_set_lr_max_diff, d) }
+
+int ss_set_profiling(ss_engine *e, int32_t enabled) {
+  if (!e) return fail(SS_ERR_INVALID, "null engine");
+  if (enabled && e->nlanes > 1) { int r = ss_synchronize(e); if (r) return r; } // lane 0 alone from here on
+  e->profiling = enabled != 0;
+  return core_set_profiling(e->lane[0], enabled);
+}
+int ss_get_stage_times(ss_engine *e, const char **names, float *ms, int32_t capacity, int32_t *count, int32_t *frames) {
+  return e ? core_get_stage_times(e->lane[0], names, ms, capacity, count, frames) : fail(SS_ERR_INVALID, "null engine");
 }
 
 } // extern "C"

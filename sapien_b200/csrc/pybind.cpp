@@ -159,7 +159,7 @@ public:
                     uint8_t bfHeight, uint8_t p1, uint8_t p2, uint8_t uniqRatio, int lrMaxDiff, uint8_t mfSize, F32 mapLx,
                     F32 mapLy, F32 mapRx, F32 mapRy, F32 a1, F32 a2, F32 a3, float b1, float b2,
                     float b3, bool dilation, float mainFx, float mainFy, float mainSkew, float mainCx,
-                    float mainCy, int device, int batch, bool keepStages, bool batched, py::object calibration) {
+                    float mainCy, int device, int batch, bool keepStages, bool batched, py::object calibration, int lanes) {
     ss_config c{};
     c.rows = rows; c.cols = cols; c.rgb_rows = rgbRows; c.rgb_cols = rgbCols;
     c.focal_len = focalLen; c.baseline_len = baselineLen; c.min_depth = minDepth; c.max_depth = maxDepth;
@@ -170,7 +170,7 @@ public:
     c.lr_max_diff = lrMaxDiff; c.mf_size = mfSize; c.b1 = b1; c.b2 = b2; c.b3 = b3;
     c.dilation = dilation; c.main_fx = mainFx; c.main_fy = mainFy; c.main_skew = mainSkew;
     c.main_cx = mainCx; c.main_cy = mainCy; c.registration = 1;
-    c.device = device; c.batch = batch; c.keep_stages = keepStages;
+    c.device = device; c.batch = batch; c.keep_stages = keepStages; c.lanes = lanes;
     const size_t n = (size_t)rows * cols;
     if (!calibration.is_none()) {
       // extension: calibration=(reg_m 3x3, rect_inv_left 3x3, rect_inv_right 3x3, (fx, fy, cx, cy)) float64 -- the planes
@@ -384,6 +384,7 @@ public:
   uint32_t outCols() const { return ocols_; }
   int device() const { return device_; }
   int batch() const { return batch_; }
+  int lanes() const { int32_t n = 1; check(ss_get_lanes(e_, &n)); return n; }
   uintptr_t cudaStream() const { void *st = nullptr; check(ss_get_stream(e_, &st)); return reinterpret_cast<uintptr_t>(st); }
 
 private:
@@ -477,14 +478,14 @@ PYBIND11_MODULE(_simsense_b200, m) {
       .def(py::init<uint32_t, uint32_t, uint32_t, uint32_t, float, float, float, float, uint64_t, float,
                     float, float, float, bool, uint8_t, uint8_t, uint32_t, uint8_t, uint8_t, uint8_t, uint8_t, uint8_t, int, uint8_t, E::F32,
                     E::F32, E::F32, E::F32, E::F32, E::F32, E::F32, float, float, float, bool, float,
-                    float, float, float, float, int, int, bool, bool, py::object>(),
+                    float, float, float, float, int, int, bool, bool, py::object, int>(),
            "rows"_a, "cols"_a, "rgb_rows"_a, "rgb_cols"_a, "focal_len"_a, "baseline_len"_a,
            "min_depth"_a, "max_depth"_a, "ir_noise_seed"_a, "speckle_shape"_a, "speckle_scale"_a,
            "gaussian_mu"_a, "gaussian_sigma"_a, "rectified"_a, "census_width"_a, "census_height"_a,
            "max_disp"_a, "bf_width"_a, "bf_height"_a, "p1"_a, "p2"_a, "uniq_ratio"_a, "lr_max_diff"_a,
            "mf_size"_a, "map_lx"_a, "map_ly"_a, "map_rx"_a, "map_ry"_a, "a1"_a, "a2"_a, "a3"_a, "b1"_a,
            "b2"_a, "b3"_a, "dilation"_a, "main_fx"_a, "main_fy"_a, "main_skew"_a, "main_cx"_a,
-           "main_cy"_a, "device"_a = -1, "batch"_a = 1, "keep_stages"_a = false, "batched"_a = false, "calibration"_a = py::none())
+           "main_cy"_a, "device"_a = -1, "batch"_a = 1, "keep_stages"_a = false, "batched"_a = false, "calibration"_a = py::none(), "lanes"_a = 0)
       .def("compute", &E::computeHost, "left_array"_a, "right_array"_a, "bbox"_a = false,
            "bbox_start_x"_a = 0, "bbox_start_y"_a = 0, "bbox_width"_a = 0, "bbox_height"_a = 0)
       .def("compute", &E::computeCuda, "left_cuda"_a, "right_cuda"_a, "bbox"_a = false,
@@ -519,5 +520,6 @@ PYBIND11_MODULE(_simsense_b200, m) {
       .def_property_readonly("output_cols", &E::outCols)
       .def_property_readonly("cuda_id", &E::device)
       .def_property_readonly("batch", &E::batch)
+      .def_property_readonly("lanes", &E::lanes)
       .def_property_readonly("cuda_stream", &E::cudaStream);
 }

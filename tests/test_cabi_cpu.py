@@ -41,7 +41,7 @@ class SsConfig(C.Structure):
                 ("b1", C.c_float), ("b2", C.c_float), ("b3", C.c_float), ("dilation", C.c_int32),
                 ("main_fx", C.c_float), ("main_fy", C.c_float), ("main_skew", C.c_float), ("main_cx", C.c_float),
                 ("main_cy", C.c_float), ("registration", C.c_int32), ("device", C.c_int32), ("batch", C.c_int32),
-                ("keep_stages", C.c_int32)]
+                ("keep_stages", C.c_int32), ("lanes", C.c_int32)]
 
 
 def good_config(**over):
