@@ -130,6 +130,8 @@ struct Core {
   bool computed = false;
   int mrows = 0, mcols = 0; // matched size of the last compute
   uint64_t frame = 0;
+  uint64_t frame_id = 0; // engine-wide frame number (set by the lane dispatcher): keys the IR-noise stream, so that
+                         // consecutive frames differ whichever lane they run on
   int launches = 0;
   // profiling
   bool profiling = false;
@@ -401,7 +403,7 @@ int compute_impl(Core *e, InputKind kind, const void *left, const void *right,
     fp.census0 = e->cen0 + (size_t)w0 * msz; fp.census1 = e->cen1 + (size_t)w0 * msz;
     fp.speckle_shape = c.speckle_shape; fp.speckle_scale = c.speckle_scale;
     fp.gaussian_mu = c.gaussian_mu; fp.gaussian_sigma = c.gaussian_sigma;
-    fp.seed = c.ir_noise_seed; fp.frame = e->frame;
+    fp.seed = c.ir_noise_seed; fp.frame = e->frame_id;
     if (c.registration && w0 == 0) { // the canvas of the whole batch is filled by the first wave's front-end
       fp.canvas = e->canvas; fp.canvas_n = (size_t)c.batch * e->rsz(); fp.canvas_fill = c.max_depth;
     }
@@ -1132,6 +1134,7 @@ int ss_destroy(ss_engine *e) {
   DeviceGuard g(e->device);                                                                                            \
   const int ln = e->next_lane();                                                                                       \
   Core *c = e->lane[ln];                                                                                               \
+  c->frame_id = e->frames;                                                                                             \
   int r = lane_begin(e, ln);                                                                                           \
   if (r) return r;                                                                                                     \
   r = (call);                                                                                                          \
