@@ -128,6 +128,19 @@ def pin_to_gpu_numa_node(torch, local):
         pass
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line, on the real stdout."""
+    text = json.dumps(line) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, text.encode())
+
+
 def dist_setup(n_gpus):
     import torch
 
@@ -139,9 +152,15 @@ def dist_setup(n_gpus):
     if world > 1:
         import torch.distributed as dist
 
-        # NCCL's INFO log (communicator size, transports) goes to STDERR: stdout carries ONE JSON line
+        # NCCL's INFO log (communicator size, transports) is wanted, but it goes to the C-level stdout and stdout must
+        # carry ONE JSON line: fd 1 is pointed at stderr for the life of the process and the JSON line is written to
+        # the saved original stdout (emit()).
         os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        global _REAL_STDOUT
+        if _REAL_STDOUT is None:
+            sys.stdout.flush()
+            _REAL_STDOUT = os.dup(1)
+            os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return rank, world, local
 
@@ -578,7 +597,7 @@ def run_ours(args, rank, world, local):
         line["batched"] = batched
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(prm, bbox_t, args.cpu_seconds)
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_reference(args, rank, world, local):
@@ -590,7 +609,7 @@ def run_reference(args, rank, world, local):
 
     if not os.path.exists(REF_SO):
         if rank == 0:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libsimsense_ref.so not built (needs /root/reference at build time)"}))
+            emit({"impl": "reference", "unavailable": "oracle/_ref/libsimsense_ref.so not built (needs /root/reference at build time)"})
         return
     key, batch, bbox, pc, desc = WORKLOADS[args.workload]
     if args.batch:
@@ -661,7 +680,7 @@ def run_reference(args, rank, world, local):
     }
     if batched is not None:
         line["batched"] = batched
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_reference_cpu(args, rank):
@@ -677,7 +696,7 @@ def run_reference_cpu(args, rank):
             "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "note": "scalar C/OpenMP port of the reference kernels (oracle/simsense_oracle.c)"},
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():

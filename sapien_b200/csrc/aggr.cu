@@ -50,6 +50,11 @@ struct AggrArgs {
   uint32_t P1P1, P2P2;
   int uniq;
   int nsm; // SM count
+  // 12-bit storage of the two plain path volumes (out of a MODE 0 pass, aux0 / aux1 of the MODE 1 pass): a pixel's D
+  // costs take 1.5 D bytes -- D low bytes, then D/2 bytes of high nibbles -- instead of 2 D.  Storage only: the
+  // arithmetic stays on u16x2 registers, so results are bit-identical by construction.  Valid while every path cost is
+  // < 4096, i.e. cmax + P2 < 4096 (aggr_pack12_supported).
+  int pack12;
   // final pass only: after the columns < seg_end[k] of a row are finished (disparities written),
   // its consumer warp bumps progress[k]; a stream can wait on the counter (cuStreamWaitValue32) and
   // post-process / copy those columns while the pass is still running
@@ -128,6 +133,74 @@ template <int NR> __device__ __forceinline__ void st_vec(void *p, const uint32_t
   }
 }
 
+
+// ---- 12-bit packed pixels (AggrArgs::pack12) ----------------------------------------------------------
+// A lane owns 2 NR consecutive disparities: 2 NR low bytes at piece + 2 NR lane and NR bytes of high nibbles at
+// piece + D + NR lane.  Two registers (4 values) at a time: low bytes b3 b2 b1 b0, nibbles n3 n2 n1 n0.
+__device__ __forceinline__ void unpack12_quad(uint32_t lo, uint32_t hi16, uint32_t &r0, uint32_t &r1) {
+  uint32_t x = (hi16 | (hi16 << 8)) & 0x00ff00ffu; // 00 n3n2 00 n1n0
+  x = (x | (x << 4)) & 0x0f0f0f0fu;                 // 0n3 0n2 0n1 0n0
+  r0 = __byte_perm(lo, x, 0x5140);                  // (b0 | n0 << 8) | (b1 | n1 << 8) << 16
+  r1 = __byte_perm(lo, x, 0x7362);
+}
+__device__ __forceinline__ void pack12_quad(uint32_t r0, uint32_t r1, uint32_t &lo, uint32_t &hi16) {
+  lo = __byte_perm(r0, r1, 0x6420);
+  uint32_t x = __byte_perm(r0, r1, 0x7531);         // 0n3 0n2 0n1 0n0
+  x = (x | (x >> 4)) & 0x00ff00ffu;
+  hi16 = (x | (x >> 8)) & 0xffffu;
+}
+template <int NR> __device__ __forceinline__ void lds_unpack12(const unsigned char *piece, int D, int lane, uint32_t (&r)[NR]) {
+  if constexpr (NR == 1) {
+    const uint32_t lo = *reinterpret_cast<const uint16_t *>(piece + 2 * lane);
+    const uint32_t hi = piece[D + lane];
+    const uint32_t x = (hi | (hi << 4)) & 0x0f0fu;
+    r[0] = __byte_perm(lo, x, 0x5140);
+  } else {
+    uint32_t lo[NR / 2], hi[(NR + 3) / 4];
+    const unsigned char *pl = piece + 2 * NR * lane, *ph = piece + D + NR * lane;
+    if constexpr (NR == 2) { lo[0] = *reinterpret_cast<const uint32_t *>(pl); hi[0] = *reinterpret_cast<const uint16_t *>(ph); }
+    else if constexpr (NR == 4) { const uint2 v = *reinterpret_cast<const uint2 *>(pl); lo[0] = v.x; lo[1] = v.y; hi[0] = *reinterpret_cast<const uint32_t *>(ph); }
+    else {
+#pragma unroll
+      for (int i = 0; i < NR / 8; ++i) {
+        const uint4 v = reinterpret_cast<const uint4 *>(pl)[i];
+        lo[4 * i] = v.x; lo[4 * i + 1] = v.y; lo[4 * i + 2] = v.z; lo[4 * i + 3] = v.w;
+        const uint2 h = reinterpret_cast<const uint2 *>(ph)[i];
+        hi[2 * i] = h.x; hi[2 * i + 1] = h.y;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NR / 2; ++q) unpack12_quad(lo[q], (hi[q / 2] >> (16 * (q & 1))) & 0xffffu, r[2 * q], r[2 * q + 1]);
+  }
+}
+template <int NR> __device__ __forceinline__ void st_pack12(unsigned char *piece, int D, int lane, const uint32_t (&r)[NR]) {
+  if constexpr (NR == 1) {
+    *reinterpret_cast<uint16_t *>(piece + 2 * lane) = (uint16_t)__byte_perm(r[0], 0u, 0x4420);
+    const uint32_t x = __byte_perm(r[0], 0u, 0x4431); // 0n1 0n0
+    piece[D + lane] = (unsigned char)((x | (x >> 4)) & 0xffu);
+  } else {
+    uint32_t lo[NR / 2], hi[(NR + 3) / 4];
+#pragma unroll
+    for (int i = 0; i < (NR + 3) / 4; ++i) hi[i] = 0;
+#pragma unroll
+    for (int q = 0; q < NR / 2; ++q) {
+      uint32_t h;
+      pack12_quad(r[2 * q], r[2 * q + 1], lo[q], h);
+      hi[q / 2] |= h << (16 * (q & 1));
+    }
+    unsigned char *pl = piece + 2 * NR * lane, *ph = piece + D + NR * lane;
+    if constexpr (NR == 2) { *reinterpret_cast<uint32_t *>(pl) = lo[0]; *reinterpret_cast<uint16_t *>(ph) = (uint16_t)hi[0]; }
+    else if constexpr (NR == 4) { *reinterpret_cast<uint2 *>(pl) = make_uint2(lo[0], lo[1]); *reinterpret_cast<uint32_t *>(ph) = hi[0]; }
+    else {
+#pragma unroll
+      for (int i = 0; i < NR / 8; ++i) {
+        reinterpret_cast<uint4 *>(pl)[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+        reinterpret_cast<uint2 *>(ph)[i] = make_uint2(hi[2 * i], hi[2 * i + 1]);
+      }
+    }
+  }
+}
+
 // One SGM path step on packed u16x2 registers (aggr.cu:39-76 of the reference):
 //   L'(d) = C(d) + min(L(d), L(d-1)+P1, L(d+1)+P1, m+P2) - m,   m = min_k L(k).
 // selUp / selDn are per-lane PRMT selectors: 0x5432 = take the neighbour lane's half, 0x5454 /
@@ -184,6 +257,11 @@ template <int NS, int K, int NCH> struct PathRing {
   const char *g[3];
   long sstride;
   int steps, PIECE, STREAM, lane;
+  // streams 1.. (aux0, aux1) when they are 12-bit packed: PX = 1.5 D bytes per pixel (rows of a chunk lie at pitch PX
+  // inside the chunk slot), xstride = byte stride between steps, c0x = tensor column of the path; else the stream-0 values
+  int PX;
+  long xstride;
+  int c0x;
   bool vertical, hrev;
   // 2-D tensor-copy mode of vertical paths: box = K rows x one pixel's D costs
   const CUtensorMap *tm;
@@ -207,27 +285,27 @@ template <int NS, int K, int NCH> struct PathRing {
       // pass).  The box is always K rows: rows past the path's end belong to the neighbouring
       // environment or are out of bounds (zero filled) and are never consumed.
       if (lane == 0) {
-        mbar_expect_tx(bar, (uint32_t)(K * PIECE * NS));
+        mbar_expect_tx(bar, (uint32_t)(K * (PIECE + (NS - 1) * PX)));
         const int c1 = vrev ? row0 - s0 - (K - 1) : row0 + s0;
 #pragma unroll
-        for (int i = 0; i < NS; ++i) tma_g2s_2d(dst + i * STREAM, tm + i, c0, c1, bar);
+        for (int i = 0; i < NS; ++i) tma_g2s_2d(dst + i * STREAM, tm + i, i ? c0x : c0, c1, bar);
       }
       return;
     }
-    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(kc * PIECE * NS));
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(kc * (PIECE + (NS - 1) * PX)));
     __syncwarp();
     if (vertical) {
       if (lane < kc) {
-        const long off = (long)(s0 + lane) * sstride;
-        const uint32_t d = dst + (uint32_t)(lane * PIECE);
+        bulk_g2s(dst + (uint32_t)(lane * PIECE), g[0] + (long)(s0 + lane) * sstride, (uint32_t)PIECE, bar);
 #pragma unroll
-        for (int i = 0; i < NS; ++i) bulk_g2s(d + i * STREAM, g[i] + off, (uint32_t)PIECE, bar);
+        for (int i = 1; i < NS; ++i)
+          bulk_g2s(dst + i * STREAM + (uint32_t)(lane * PX), g[i] + (long)(s0 + lane) * xstride, (uint32_t)PX, bar);
       }
     } else if (lane == 0) {
-      const long off = (long)(hrev ? s0 + kc - 1 : s0) * sstride;
-      const uint32_t bytes = (uint32_t)(kc * PIECE);
+      const long at = hrev ? s0 + kc - 1 : s0;
+      bulk_g2s(dst, g[0] + at * sstride, (uint32_t)(kc * PIECE), bar);
 #pragma unroll
-      for (int i = 0; i < NS; ++i) bulk_g2s(dst + i * STREAM, g[i] + off, bytes, bar);
+      for (int i = 1; i < NS; ++i) bulk_g2s(dst + i * STREAM, g[i] + at * xstride, (uint32_t)(kc * PX), bar);
     }
   }
 };
@@ -251,9 +329,12 @@ __device__ __forceinline__ PathGeom path_geom(const AggrArgs &a, long path) {
 }
 
 // ---- MODE 0 / 1: one independent warp per path ---------------------------------------------------
-template <int NR, int MODE, bool PARTIAL, bool DBG, int K, int NCH>
+// PACK: the plain path volumes are stored 12-bit packed (AggrArgs::pack12): MODE 0 packs its output, MODE 1 unpacks
+// aux0 / aux1; the cost volume and the MODE 1 output (a sum of three paths, up to 14 bits) stay u16.
+template <int NR, int MODE, bool PARTIAL, bool DBG, int K, int NCH, bool PACK>
 __global__ void __launch_bounds__(128) aggr_kernel(const __grid_constant__ AggrArgs a) {
   static_assert(MODE == 0 || MODE == 1, "plain passes only");
+  static_assert(!(PACK && DBG), "stage materialisation keeps u16 volumes");
   constexpr int DPL = 2 * NR;
   constexpr int NS = nstream<MODE>();
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -272,12 +353,17 @@ __global__ void __launch_bounds__(128) aggr_kernel(const __grid_constant__ AggrA
   pr.bar0 = (uint32_t)__cvta_generic_to_shared(wsm);
   pr.ring_s = pr.bar0 + lay.ring;
   pr.g[0] = reinterpret_cast<const char *>(a.C + pg.e0);
-  pr.g[1] = NS > 1 ? reinterpret_cast<const char *>(a.aux0 + pg.e0) : nullptr;
-  pr.g[2] = NS > 2 ? reinterpret_cast<const char *>(a.aux1 + pg.e0) : nullptr;
+  constexpr bool PACKIN = PACK && MODE == 1; // aux streams arrive packed
+  const int PX = PACKIN ? (D * 3) / 2 : PIECE;
+  const size_t xoff = PACKIN ? pg.e0 * 3 / 2 : pg.e0 * 2; // byte offset of the path's first pixel in an aux volume
+  pr.g[1] = NS > 1 ? reinterpret_cast<const char *>(a.aux0) + xoff : nullptr;
+  pr.g[2] = NS > 2 ? reinterpret_cast<const char *>(a.aux1) + xoff : nullptr;
   pr.sstride = pg.sstride; pr.steps = steps; pr.PIECE = PIECE; pr.STREAM = NCH * K * PIECE; pr.lane = lane;
+  pr.PX = PX; pr.xstride = PACKIN ? pg.sstride * 3 / 4 : pg.sstride;
   pr.vertical = a.vertical != 0; pr.hrev = !a.vertical && a.reverse;
   pr.tm = a.tm; pr.tma = a.tma && a.vertical; pr.vrev = a.reverse;
   pr.c0 = pg.q * D; pr.row0 = pg.n * a.rows + (a.reverse ? a.rows - 1 : 0);
+  pr.c0x = PACKIN ? pg.q * ((D * 3) / 4) : pr.c0;
   const unsigned char *ring = wsm + lay.ring;
   const int STREAM = pr.STREAM;
   const bool hrev = pr.hrev || (pr.tma && a.reverse); // chunk rows lie in ascending address order: walk them backwards
@@ -303,18 +389,26 @@ __global__ void __launch_bounds__(128) aggr_kernel(const __grid_constant__ AggrA
   uint32_t L[NR];
 #pragma unroll
   for (int r = 0; r < NR; ++r) L[r] = active ? 0u : 0xffffffffu;
-  char *pOut = reinterpret_cast<char *>(a.out + pg.e0) + loff;
+  constexpr bool PACKOUT = PACK && MODE == 0; // the output volume is written packed
+  char *pOut = PACKOUT ? reinterpret_cast<char *>(a.out) + pg.e0 * 3 / 2 : reinterpret_cast<char *>(a.out + pg.e0) + loff;
   char *pDbg0 = DBG ? reinterpret_cast<char *>(a.dbg0 + pg.e0) + loff : nullptr;
   const long sstride = pg.sstride;
+  const long ostride = PACKOUT ? pg.sstride * 3 / 4 : pg.sstride;
 
-  auto step = [&](const unsigned char *pc) {
+  // pc: this lane's slice of the cost row; px: start of the same step's row in the first aux stream (PACKIN only)
+  auto step = [&](const unsigned char *pc, const unsigned char *px) {
     uint32_t c[NR], x0[NR], x1[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) { c[r] = 0; x0[r] = 0; x1[r] = 0; }
     if (active) {
       lds_vec<NR>(pc, c);
-      if (NS > 1) lds_vec<NR>(pc + STREAM, x0);
-      if (NS > 2) lds_vec<NR>(pc + 2 * STREAM, x1);
+      if (PACKIN) {
+        if (NS > 1) lds_unpack12<NR>(px, D, lane, x0);
+        if (NS > 2) lds_unpack12<NR>(px + STREAM, D, lane, x1);
+      } else {
+        if (NS > 1) lds_vec<NR>(pc + STREAM, x0);
+        if (NS > 2) lds_vec<NR>(pc + 2 * STREAM, x1);
+      }
     }
     sgm_step<NR>(L, c, a.P1P1, a.P2P2, selUp, selDn);
     if (PARTIAL) {
@@ -323,7 +417,8 @@ __global__ void __launch_bounds__(128) aggr_kernel(const __grid_constant__ AggrA
     }
     if (active) {
       if (MODE == 0) {
-        st_vec<NR>(pOut, L);
+        if (PACKOUT) st_pack12<NR>(reinterpret_cast<unsigned char *>(pOut), D, lane, L);
+        else st_vec<NR>(pOut, L);
       } else {
         uint32_t o[NR];
 #pragma unroll
@@ -332,7 +427,7 @@ __global__ void __launch_bounds__(128) aggr_kernel(const __grid_constant__ AggrA
         if (DBG) st_vec<NR>(pDbg0, L);
       }
     }
-    pOut += sstride;
+    pOut += ostride;
     if (DBG) pDbg0 += sstride;
   };
 
@@ -343,19 +438,20 @@ __global__ void __launch_bounds__(128) aggr_kernel(const __grid_constant__ AggrA
     if (ci + NCH - 1 < nchunks) pr.issue(ci + NCH - 1); // refills the slot consumed one chunk ago
     const int kc = min(K, steps - ci * K);
     const unsigned char *pc = ring + slot * K * PIECE + loff;
+    const unsigned char *px = ring + STREAM + slot * K * PIECE; // (packed aux rows lie at pitch PX inside the slot)
     if (kc == K) {
       if (hrev) {
-        pc += (K - 1) * PIECE;
+        pc += (K - 1) * PIECE; px += (K - 1) * PX;
 #pragma unroll
-        for (int k = 0; k < K; ++k) { step(pc); pc -= PIECE; }
+        for (int k = 0; k < K; ++k) { step(pc, px); pc -= PIECE; px -= PX; }
       } else {
 #pragma unroll
-        for (int k = 0; k < K; ++k) { step(pc); pc += PIECE; }
+        for (int k = 0; k < K; ++k) { step(pc, px); pc += PIECE; px += PX; }
       }
     } else {
-      const int dp = hrev ? -PIECE : PIECE;
-      if (hrev) pc += ((pr.tma ? K : kc) - 1) * PIECE; // a tensor box is always K rows, a bulk piece kc steps
-      for (int k = 0; k < kc; ++k) { step(pc); pc += dp; }
+      const int dp = hrev ? -PIECE : PIECE, dx = hrev ? -PX : PX;
+      if (hrev) { pc += ((pr.tma ? K : kc) - 1) * PIECE; px += ((pr.tma ? K : kc) - 1) * PX; } // a tensor box is always K rows, a bulk piece kc steps
+      for (int k = 0; k < kc; ++k) { step(pc, px); pc += dp; px += dx; }
     }
     if (++slot == NCH) { slot = 0; parity ^= 1; }
   }
@@ -433,6 +529,7 @@ __global__ void __launch_bounds__(512, 1) aggr_wta_kernel(const __grid_constant_
     pr.g[2] = nullptr;
     pr.sstride = pg.sstride; pr.steps = steps; pr.PIECE = PIECE; pr.STREAM = NCH * K * PIECE; pr.lane = lane;
     pr.vertical = false; pr.hrev = false; pr.tma = 0; pr.tm = nullptr; pr.c0 = pr.row0 = pr.vrev = 0;
+    pr.PX = PIECE; pr.xstride = pg.sstride; pr.c0x = 0;
     const unsigned char *ring = wsm + lay.ring;
     const int STREAM = pr.STREAM;
     const uint32_t selUp = lane == 0 ? 0x5454u : 0x5432u;
@@ -676,7 +773,20 @@ static bool make_volume_map(CUtensorMap *tm, const uint16_t *base, int N, int ro
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int NR, int MODE, bool PARTIAL, bool DBG, int NCHO = 0>
+// 12-bit packed volume [N][rows][cols][1.5 D bytes] as a 2-D u16 tensor [N*rows][cols * 0.75 D], box = K rows x 0.75 D
+static bool make_volume_map12(CUtensorMap *tm, const uint16_t *base, int N, int rows, int cols, int D, int K) {
+  TensorMapEncodeTiledFn enc = tensor_map_encoder();
+  if (!enc || !base) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols * (D * 3 / 4), (cuuint64_t)N * rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)cols * (D * 3 / 2)};
+  const cuuint32_t box[2] = {(cuuint32_t)(D * 3 / 4), (cuuint32_t)K};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<uint16_t *>(base), gdim, gstride, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int NR, int MODE, bool PARTIAL, bool DBG, int NCHO = 0, bool PACK = false>
 static cudaError_t launch_one(const AggrArgs &a_in, cudaStream_t st) {
   AggrArgs a = a_in;
   a.tma = 0;
@@ -686,6 +796,7 @@ static cudaError_t launch_one(const AggrArgs &a_in, cudaStream_t st) {
   const long npaths = (long)a.N * (a.vertical ? a.cols : a.rows);
   cudaError_t e;
   if constexpr (MODE == 2) {
+    static_assert(!PACK, "the final pass reads u16 volumes");
     auto k = aggr_wta_kernel<NR, PARTIAL, DBG, K, NCH>;
     // rows per block: enough for one resident wave with one block per SM when shared memory allows
     // (<= 5 rows in the latency-bound single-frame regime; up to 8 with the 2-slot rings of the
@@ -704,11 +815,13 @@ static cudaError_t launch_one(const AggrArgs &a_in, cudaStream_t st) {
     // than as bulk pieces: C3 top->bottom 1.61 ms vs 1.74 ms)
     if (a.vertical && a.D <= 256 && a.D * 2 % 128 == 0 && (long)a.N * a.rows < 0x7fffffffL) {
       bool ok = make_volume_map(&a.tm[0], a.C, a.N, a.rows, a.cols, a.D, K);
-      if (MODE == 1) ok = ok && make_volume_map(&a.tm[1], a.aux0, a.N, a.rows, a.cols, a.D, K) &&
-                            make_volume_map(&a.tm[2], a.aux1, a.N, a.rows, a.cols, a.D, K);
+      if (MODE == 1 && !PACK) ok = ok && make_volume_map(&a.tm[1], a.aux0, a.N, a.rows, a.cols, a.D, K) &&
+                                     make_volume_map(&a.tm[2], a.aux1, a.N, a.rows, a.cols, a.D, K);
+      if (MODE == 1 && PACK) ok = ok && make_volume_map12(&a.tm[1], a.aux0, a.N, a.rows, a.cols, a.D, K) &&
+                                    make_volume_map12(&a.tm[2], a.aux1, a.N, a.rows, a.cols, a.D, K);
       a.tma = ok ? 1 : 0;
     }
-    auto k = aggr_kernel<NR, MODE, PARTIAL, DBG, K, NCH>;
+    auto k = aggr_kernel<NR, MODE, PARTIAL, DBG, K, NCH, PACK>;
     if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     k<<<(unsigned)npaths, 32, smem, st>>>(a);
   }
@@ -721,11 +834,20 @@ template <int MODE, int NCHO = 0> static cudaError_t dispatch(const AggrArgs &a,
   const int nr = nr_for(a.D);
   const bool partial = a.D != 64 * nr;
   const bool dbg = MODE != 0 && a.dbg0 != nullptr;
+  const bool pack = MODE != 2 && a.pack12 && !dbg;
 #define SSB_CASE(NRV)                                                                             \
   case NRV:                                                                                       \
-    if (MODE == 0) return partial ? launch_one<NRV, MODE, true, false, NCHO>(a, st) : launch_one<NRV, MODE, false, false, NCHO>(a, st); \
-    if (dbg) return partial ? launch_one<NRV, MODE, true, true>(a, st) : launch_one<NRV, MODE, false, true>(a, st);  \
-    return partial ? launch_one<NRV, MODE, true, false, (MODE == 2 ? NCHO : 0)>(a, st) : launch_one<NRV, MODE, false, false, (MODE == 2 ? NCHO : 0)>(a, st);
+    if constexpr (MODE == 0) {                                                                    \
+      if (pack) return partial ? launch_one<NRV, 0, true, false, NCHO, true>(a, st) : launch_one<NRV, 0, false, false, NCHO, true>(a, st); \
+      return partial ? launch_one<NRV, 0, true, false, NCHO>(a, st) : launch_one<NRV, 0, false, false, NCHO>(a, st); \
+    } else if constexpr (MODE == 1) {                                                             \
+      if (dbg) return partial ? launch_one<NRV, 1, true, true>(a, st) : launch_one<NRV, 1, false, true>(a, st); \
+      if (pack) return partial ? launch_one<NRV, 1, true, false, 0, true>(a, st) : launch_one<NRV, 1, false, false, 0, true>(a, st); \
+      return partial ? launch_one<NRV, 1, true, false>(a, st) : launch_one<NRV, 1, false, false>(a, st); \
+    } else {                                                                                      \
+      if (dbg) return partial ? launch_one<NRV, 2, true, true>(a, st) : launch_one<NRV, 2, false, true>(a, st); \
+      return partial ? launch_one<NRV, 2, true, false, NCHO>(a, st) : launch_one<NRV, 2, false, false, NCHO>(a, st); \
+    }
   switch (nr) {
     SSB_CASE(1) SSB_CASE(2) SSB_CASE(4) SSB_CASE(8) SSB_CASE(16)
   }
@@ -748,6 +870,14 @@ bool aggr_fast_supported(int D, int cmax, int P1, int P2) {
   return 4L * ((long)cmax + P2) <= 65535L && (long)cmax + P2 + P1 <= 65535L;
 }
 
+bool aggr_pack12_supported(int D, int cmax, int P2) {
+  // every path cost is at most cmax + P2 (aggr.cu:39-76: L <= C + P2).  A packed pixel (1.5 D bytes) must be a whole
+  // number of 32-byte sectors, else the vertical passes touch sectors they do not own: D = 96 (144-byte pixels)
+  // measured 8.5 % SLOWER packed (C3, 16 envs: 3.04 -> 3.32 ms), D = 64 / 256 4-5 % faster (C4 55.1 -> 57.4 k
+  // env-frames/s, C5 467 -> 492 frames/s), D = 128 neutral at two lanes (profiles/r02_pack12_ab.md).
+  return D % 64 == 0 && (long)cmax + P2 < 4096;
+}
+
 static cudaError_t common_args(AggrArgs &a, const AggrBuffers &b, int N, int rows, int cols, int D, int P1, int P2, int uniq) {
   if ((long)N * (rows > cols ? rows : cols) > 0x7fffffffL) return cudaErrorInvalidValue;
   a.C = b.C;
@@ -756,6 +886,7 @@ static cudaError_t common_args(AggrArgs &a, const AggrBuffers &b, int N, int row
   a.P2P2 = (uint32_t)P2 * 0x10001u;
   a.uniq = uniq;
   a.nsm = sm_count();
+  a.pack12 = b.pack12;
   return cudaSuccess;
 }
 

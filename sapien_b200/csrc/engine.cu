@@ -128,6 +128,7 @@ struct Core {
   uint16_t *dispR = nullptr;
   int wave = 1;
   bool computed = false;
+  bool last_pack12 = false; // the last frame stored L1 / L2 12-bit packed (ss_get_stage_host unpacks)
   int mrows = 0, mcols = 0; // matched size of the last compute
   uint64_t frame = 0;
   uint64_t frame_id = 0; // engine-wide frame number (set by the lane dispatcher): keys the IR-noise stream, so that
@@ -254,7 +255,7 @@ int create_impl(Core *e, const float *mapLx, const float *mapLy, const float *ma
   // (configurations outside the packed-u16 regime aggregate through generic.cu, which needs three more volumes)
   const bool fast0 = aggr_fast_supported(c.max_disp, census_bits(c.census_width, c.census_height) * c.bf_width * c.bf_height,
                                          c.p1 * c.bf_width * c.bf_height, c.p2 * c.bf_width * c.bf_height);
-  const int nvol = c.keep_stages ? 7 : (fast0 ? 3 : 6);
+  const int nvol = c.keep_stages ? 7 : (fast0 ? 4 : 6); // C, L1, L2, S3 (S3 is its own volume: L1 / L2 may be 12-bit packed)
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   const size_t small = N * (fsz * 42 + e->rsz() * 52) + (64u << 20);
@@ -265,12 +266,8 @@ int create_impl(Core *e, const float *mapLx, const float *mapLy, const float *ma
   if ((r = e->alloc(&e->C, wv))) return r;
   if ((r = e->alloc(&e->L1, wv))) return r;
   if ((r = e->alloc(&e->L2, wv))) return r;
-  if (c.keep_stages) {
-    if ((r = e->alloc(&e->S3, wv))) return r;
-    if ((r = e->ensure_generic_volumes())) return r;
-  } else {
-    e->S3 = e->L2;
-  }
+  if ((r = e->alloc(&e->S3, wv))) return r;
+  if (c.keep_stages && (r = e->ensure_generic_volumes())) return r;
   for (int k = 0; k < 2; ++k) {
     if ((r = e->alloc(&e->raw0s[k], N * fsz))) return r;
     if ((r = e->alloc(&e->raw1s[k], N * fsz))) return r;
@@ -297,6 +294,9 @@ int create_impl(Core *e, const float *mapLx, const float *mapLy, const float *ma
 }
 
 enum InputKind { IN_U8, IN_RGBA };
+
+// debug hook (not part of include/ss_b200.h): 0 turns the 12-bit storage of the path volumes off (A/B measurements)
+int g_allow_pack12 = 1;
 
 // host_left / host_right: when non-null (host-u8 path, one wave, 7x7 census) the uploads happen here,
 // the right image on the helper stream, so that the left image's front-end overlaps the second upload
@@ -355,6 +355,8 @@ int compute_impl(Core *e, InputKind kind, const void *left, const void *right,
   const int cmax = census_bits(c.census_width, c.census_height) * c.bf_width * c.bf_height;
   const bool fast = aggr_fast_supported(D, cmax, P1, P2);
   if (!fast) { int r = e->ensure_generic_volumes(); if (r) return r; }
+  const int pack12 = fast && !c.keep_stages && g_allow_pack12 && aggr_pack12_supported(D, cmax, P2);
+  e->last_pack12 = pack12 != 0;
   const size_t fsz = e->fsz(), msz = (size_t)rows * cols;
   int launches = 0;
   // Banded output plan (see ss_bind_output_host): up to 4 progress points of the final pass -> up to 5 bands
@@ -466,6 +468,7 @@ int compute_impl(Core *e, InputKind kind, const void *left, const void *right,
     ab.C = e->C; ab.L1 = e->L1; ab.L2 = e->L2; ab.S3 = e->S3;
     ab.dbgL0 = e->dbgL0; ab.dbgL3 = e->dbgL3; ab.dbgLAll = e->dbgLAll;
     ab.dispL = e->dispL + (size_t)w0 * msz; ab.dispR = e->dispR + (size_t)w0 * msz;
+    ab.pack12 = pack12;
     if (fast) {
       if (!c.keep_stages) { ab.dbgL0 = ab.dbgL3 = ab.dbgLAll = nullptr; }
       AggrMarks am{[](void *ctx, const char *name) { static_cast<Core *>(ctx)->mark(name); }, e};
@@ -514,6 +517,7 @@ int compute_impl(Core *e, InputKind kind, const void *left, const void *right,
     AggrBuffers ab{};
     ab.C = e->C; ab.L1 = e->L1; ab.L2 = e->L2; ab.S3 = e->S3;
     ab.dispL = e->dispL; ab.dispR = e->dispR;
+    ab.pack12 = pack12;
     const int H = c.mf_size / 2, ocols = (int)e->out_cols(), orows = (int)e->out_rows();
     const size_t pitch = (size_t)ocols * sizeof(float);
     { int r = join_prev_bands(); if (r) return r; } // (also: nobody polls the progress counters any more)
@@ -590,6 +594,8 @@ int compute_impl(Core *e, InputKind kind, const void *left, const void *right,
 }
 
 } // namespace
+
+extern "C" int ssb_debug_set_pack12(int on) { g_allow_pack12 = on; return 0; }
 
 // Host-facing calls that read results through the main stream first join whatever an asynchronous frame left on the
 // helper and copy streams (its column bands and their copies).
@@ -971,6 +977,20 @@ static int core_get_stage_host(Core *e, const char *name, int32_t index, void *o
   if (r) return r;
   if (bytes) *bytes = sz;
   if (cap < sz) return fail(SS_ERR_INVALID, "output buffer too small");
+  if (n == "L1" && e->last_pack12) { // 12-bit packed on the device (1.5 D bytes per pixel): unpack on the host
+    const size_t pb = D * 3 / 2;
+    std::vector<unsigned char> tmp(msz * pb);
+    CK(cudaMemcpyAsync(tmp.data(), reinterpret_cast<const unsigned char *>(e->L1) + (size_t)index * msz * pb, tmp.size(),
+                       cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    uint16_t *o = static_cast<uint16_t *>(out);
+    for (size_t p = 0; p < msz; ++p)
+      for (size_t d = 0; d < D; ++d) {
+        const unsigned nib = (tmp[p * pb + D + d / 2] >> (4 * (d & 1))) & 0xfu;
+        o[p * D + d] = (uint16_t)(tmp[p * pb + d] | (nib << 8));
+      }
+    return SS_OK;
+  }
   CK(cudaMemcpyAsync(out, src, sz, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   return SS_OK;

@@ -53,11 +53,14 @@ cudaError_t launch_cost(const uint32_t *cL, const uint32_t *cR, uint16_t *C, int
 // ----------------------------------------------------------------------------- aggr.cu
 // true when the packed-u16 DPX path is valid for this configuration
 bool aggr_fast_supported(int D, int cmax, int P1, int P2);
+// true when the two plain path volumes (L1, L2) may be stored 12-bit packed (1.5 D bytes per pixel)
+bool aggr_pack12_supported(int D, int cmax, int P2);
 struct AggrBuffers {
   const uint16_t *C; // cost volume
   uint16_t *L1;      // right->left path
   uint16_t *L2;      // top->bottom path
-  uint16_t *S3;      // L1+L2+L3 (may alias L2)
+  uint16_t *S3;      // L1+L2+L3 (may alias L2 unless pack12)
+  int pack12;        // L1 / L2 hold 12-bit packed pixels (fast path without stage materialisation only); S3 must not alias L2
   uint16_t *dbgL0, *dbgL3, *dbgLAll; // optional (keep_stages), else null
   float *dispL;      // [N][rows][cols] WTA left disparity (uniqueness + sub-pixel), -1 invalid
   uint16_t *dispR;   // [N][rows][cols] WTA right disparity

@@ -486,3 +486,24 @@ def test_pipelined_host_frames_generic_census(native):
         eng.wait(tickets[i])
         solo.compute(*pairs[i])
         assert np.array_equal(outs[i % 2].view(np.uint32), solo.get_ndarray().view(np.uint32))
+
+
+@pytest.mark.parametrize("over", [dict(max_disp=64), dict(max_disp=96), dict(max_disp=128), dict(max_disp=256),
+                                  dict(max_disp=64, p1=20, p2=59), dict(max_disp=128, p1=30, p2=60)])
+def test_packed_path_volumes_vs_oracle(native, oracle, over):
+    """Production engines store the two plain path volumes (L1, L2) 12-bit packed when cmax + P2 < 4096 (storage only).
+    L1 read back through ss_get_stage_host (unpacked on the host) and everything downstream must equal the oracle --
+    one / two / four registers per lane, the partial-lane D = 96 case, and penalties just below (p2 = 59: 1176 + 2891 =
+    4067) and just above (p2 = 60: 4116, packing off) the 12-bit limit."""
+    prm = variant(configs._sensor_params("D415", max_disp=64, rectified=True, scale=(320, 120, 320, 120)), **over)
+    left, right = configs.pair(prm, seed=prm.max_disp + prm.p2)
+    ref = oracle.pipeline(prm, left, right)
+    eng = make_engine(native, prm)
+    eng.compute(left, right)
+    assert np.array_equal(get_stage(eng, prm, "L1"), ref["L1"])
+    assert_stages_equal(eng, prm, ref, names=FAST_STAGES)
+    assert_depth_close(eng.get_ndarray(), ref["out"])
+    batch = make_engine(native, prm, batch=3)
+    batch.compute(np.stack([left, right, left]), np.stack([right, left, right]))
+    assert np.array_equal(get_stage(batch, prm, "L1", index=2), ref["L1"])
+    assert np.array_equal(batch.get_ndarray()[0].view(np.uint32), eng.get_ndarray().view(np.uint32))
