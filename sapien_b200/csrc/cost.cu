@@ -284,6 +284,7 @@ __global__ void cost_generic_kernel(const uint32_t *__restrict__ cL, const uint3
   C[idx] = (uint16_t)acc;
 }
 
+static int g_cost_bpsm = 0; // experiment hook: cap on resident blocks per SM the grid is sized for (0 = occupancy)
 template <int BW, int BH, int TX, int NS, int TD, bool PACK8, int DT = 0>
 static cudaError_t launch_cfg(const uint32_t *cL, const uint32_t *cR, uint16_t *C, int N, int rows,
                               int cols, int D, cudaStream_t st) {
@@ -294,6 +295,7 @@ static cudaError_t launch_cfg(const uint32_t *cL, const uint32_t *cR, uint16_t *
   if ((e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
   int per_sm = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, TD * NS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  if (g_cost_bpsm > 0 && per_sm > g_cost_bpsm) per_sm = g_cost_bpsm;
   const int nchunks = (D + 2 * TD - 1) / (2 * TD);
   const long xb = (long)((cols + NS * TX - 1) / (NS * TX)) * nchunks;
   // Row bands: as many as fit in ONE resident wave (a second, partial wave would double the
@@ -333,6 +335,7 @@ static cudaError_t launch_fast(const uint32_t *cL, const uint32_t *cR, uint16_t 
 }
 
 } // namespace ssb
+extern "C" int ssb_debug_set_cost_bpsm(int v) { ssb::g_cost_bpsm = v; return 0; }
 extern "C" int ssb_debug_set_cost_trace(void *device_buffer) {
   return (int)cudaMemcpyToSymbol(ssb::g_cost_trace, &device_buffer, sizeof(device_buffer));
 }
