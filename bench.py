@@ -308,7 +308,7 @@ def batched_ours(args, rank, world, local):
     steps = max(3, min(args.steps, 10))
     # ---- C4: 1024 envs x 256x256, D=64, env_range(1024, rank, world) per rank: strong scaling ----
     prm = configs.params("C4")
-    pipes = args.pipelines or 2
+    pipes = args.pipelines or 1  # (2-4 concurrent sub-batches measured no faster on C3 / C4: batched kernels fill the GPU)
     sh = sharding.ShardedStereoDepth(prm.engine_args(), args.c4_envs, rank, world, device=local, pipelines=pipes)
     sets = c4_inputs(prm, sh.start, sh.stop, 2, torch)
     ms = time_sharded(sh, sets, steps, 2, torch, world)
