@@ -93,7 +93,7 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for line in self.f:
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
@@ -103,13 +103,22 @@ class ClockSampler:
                 mx.append(float(c[2]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(c[3]))
+            except ValueError:
+                pw.append(0.0)
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         self.f.close()
         os.unlink(self.f.name)
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+            # the sampled span also holds host-side set-up between the timed regions: "under load" = the samples whose
+            # power draw is at least half way between the lowest and the highest one seen
+            lo, hi = min(pw), max(pw)
+            load = [s for s, p in zip(sm, pw) if p >= lo + 0.5 * (hi - lo)] or sm
+            out.update(sm_mhz=float(np.median(load)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm),
+                       samples_under_load=len(load), power_w_max=hi)
         return out
 
 
@@ -155,7 +164,7 @@ def dist_setup(n_gpus):
         # NCCL's INFO log (communicator size, transports) is wanted, but it goes to the C-level stdout and stdout must
         # carry ONE JSON line: fd 1 is pointed at stderr for the life of the process and the JSON line is written to
         # the saved original stdout (emit()).
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ["NCCL_DEBUG"] = os.environ.get("SSB_NCCL_DEBUG", "INFO")  # (the image presets NCCL_DEBUG=VERSION)
         global _REAL_STDOUT
         if _REAL_STDOUT is None:
             sys.stdout.flush()
@@ -451,6 +460,8 @@ def run_ours(args, rank, world, local):
             eng.get_rgb_point_cloud_cuda(rgba)
 
     torch.cuda.synchronize()
+    sampler = ClockSampler(local)  # 100 ms samples from the warm-up to the end of the batched block (each timed region is short)
+    sampler.start()
     for i in range(args.warmup):
         step(i)
     stream.synchronize()
@@ -463,18 +474,18 @@ def run_ours(args, rank, world, local):
     stages = dict(eng.get_stage_times())
     eng.set_profiling(False)
     barrier(world)
-    sampler = ClockSampler(local)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    th0 = time.perf_counter()
     for i in range(args.steps):
         step(i)
+    host_us = (time.perf_counter() - th0) / args.steps * 1e6  # CPU time to enqueue one frame (the loop never waits)
     e1.record(stream)
     stream.synchronize()
     barrier(world)
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
     launches = eng.get_launches_per_compute() + (1 if pc else 0)
+    eng_lanes = eng.lanes
     ms = max_over_ranks(ms, world)
     frames = batch * args.steps * world
     value = frames / (ms / 1e3)
@@ -545,8 +556,8 @@ def run_ours(args, rank, world, local):
            "one_frame_at_a_time": {"value": batch * e2e_steps * world / ext_s, "unit": "frames/s",
                                    "api": "extension path, synchronous: bind_output(pinned) once; per step compute(left_u8 pinned, right_u8 pinned[, bbox]) + get_ndarray(out=pinned)"},
            "strict": {"value": batch * e2e_steps * world / strict_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                      "api": "reference signature only: compute(left_u8 ndarray, right_u8 ndarray[, bbox]) + get_ndarray() -> new ndarray (pageable inputs, "
-                             "engine-owned pinned staging, one host memcpy into the returned array)"}}
+                      "api": "reference signature only: compute(left_u8 ndarray, right_u8 ndarray[, bbox]) + get_ndarray() (pageable inputs; the map is delivered "
+                             "into a page-locked array of a small pool that get_ndarray() hands out -- reused once the caller has dropped it)"}}
 
     batched = None
     del dev_sets
@@ -554,6 +565,7 @@ def run_ours(args, rank, world, local):
         del eng
         torch.cuda.empty_cache()
         batched = batched_ours(args, rank, world, local)
+    clocks = sampler.stop()
 
     if rank != 0:
         return
@@ -585,8 +597,9 @@ def run_ours(args, rank, world, local):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u16", "data": "synthetic",
         "config": shared_config(args, desc, batch, world),
-        "arm": {"impl": "sapien_b200 (this repo)", "volumes_mb": 3 * V / 1e6,
-                "pipelining": "frames enqueued back to back on the engine's stream; the front-end of frame k+1 (helper stream) overlaps the final pass / post-processing of frame k"},
+        "arm": {"impl": "sapien_b200 (this repo)", "volumes_mb": 4 * V / 1e6, "lanes": eng_lanes, "host_enqueue_us_per_frame": host_us,
+                "pipelining": "frames enqueued back to back; consecutive frames alternate between the engine's lanes (independent stream / buffer sets) and overlap on the GPU, "
+                              "results in submission order on the engine's public stream; the front-end of a frame runs under the previous frame of its lane"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches * args.steps,
         "roofline": roofline,
         "frame_roofline": {"algorithmic_bytes_per_step": int(alg), "achieved_gbs": alg / (ms / args.steps * 1e-3) / 1e9 ,
@@ -647,7 +660,6 @@ def run_reference(args, rank, world, local):
     torch.cuda.synchronize()
     barrier(world)
     ms = max_over_ranks(e0.elapsed_time(e1), world)
-    clocks = sampler.stop()
     value = batch * steps * world / (ms / 1e3)
     e2e_steps = max(3, min(steps, 20))
     out = None
@@ -664,6 +676,7 @@ def run_reference(args, rank, world, local):
     del dev_sets
     torch.cuda.empty_cache()
     batched = None if args.no_batched else batched_reference(args, rank, world, local)
+    clocks = sampler.stop()
     if rank != 0:
         return
     line = {

@@ -137,6 +137,11 @@ int ss_compute_device_u8(ss_engine *e, const void *left, const void *right, cons
 int ss_submit_host_u8(ss_engine *e, const uint8_t *left, const uint8_t *right, const ss_bbox *bbox,
                       float *out_host, size_t capacity_bytes, uint64_t *ticket);
 int ss_wait_frame(ss_engine *e, uint64_t ticket);
+/* Extension: page-locked host memory for the buffers of ss_submit_host_u8 / ss_bind_output_host, for bindings that have
+ * no CUDA runtime of their own (the Python binding hands such buffers out as the arrays get_ndarray() returns, so that a
+ * strict compute() + get_ndarray() caller gets its depth map without an extra host copy). */
+int ss_alloc_host(size_t bytes, void **ptr);
+int ss_free_host(void *ptr);
 /* Extension: orders the NEXT compute of this engine after everything already enqueued on `stream`
  * (a producer stream other than the one passed to the compute call, e.g. the `stream` entry of a
  * __cuda_array_interface__ v3 input).  No host synchronisation. */

@@ -1121,6 +1121,16 @@ extern "C" {
 const char *ss_last_error(void) { return g_err.c_str(); }
 const char *ss_version(void) { return "ss_b200 0.2 (sm_100a)"; }
 
+int ss_alloc_host(size_t bytes, void **ptr) {
+  if (!ptr || !bytes) return fail(SS_ERR_INVALID, "null argument");
+  CK(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable));
+  return SS_OK;
+}
+int ss_free_host(void *ptr) {
+  if (ptr) CK(cudaFreeHost(ptr));
+  return SS_OK;
+}
+
 int ss_pointer_device(const void *ptr, int32_t *device) {
   if (!device) return fail(SS_ERR_INVALID, "null argument");
   cudaPointerAttributes attr{};

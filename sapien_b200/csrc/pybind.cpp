@@ -209,9 +209,39 @@ public:
     checkHostShape(left, right);
     ss_bbox bb{bbox ? 1 : 0, x, y, w, h};
     const uint8_t *l = left.data(), *r = right.data();
+    // A strict compute(l, r) + get_ndarray() caller: the frame is delivered straight into a page-locked array from
+    // a small pool and get_ndarray() returns THAT array -- no staging copy, no fresh allocation.  An array is reused
+    // only when nobody but the pool references it any more, so results a caller still holds are never overwritten.
+    pool_last_ = -1;
+    pool_given_ = false;
+    float *dst = nullptr;
+    const size_t bytes = (size_t)std::max(batch_, 1) * orows_ * ocols_ * sizeof(float);
+    if (bound_.is_none() && bytes <= (64u << 20)) {
+      int slot = -1;
+      for (size_t i = 0; i < pool_.size(); ++i)
+        if (pool_[i].ref_count() == 1) { slot = (int)i; break; }
+      if (slot < 0 && pool_.size() < 4) {
+        void *p = nullptr;
+        if (ss_alloc_host(bytes, &p) == SS_OK) {
+          py::capsule owner(p, [](void *q) { ss_free_host(q); });
+          std::vector<py::ssize_t> shape{(py::ssize_t)orows_, (py::ssize_t)ocols_};
+          if (lead_) shape.insert(shape.begin(), batch_);
+          pool_.push_back(py::array_t<float>(shape, static_cast<float *>(p), owner));
+          slot = (int)pool_.size() - 1;
+        }
+      }
+      if (slot >= 0) { dst = pool_[slot].mutable_data(); pool_last_ = slot; }
+    }
     py::gil_scoped_release nogil;
-    int st = ss_compute_host_u8(e_, l, r, &bb);
-    if (st) { py::gil_scoped_acquire gil; raise_status(st); }
+    int st;
+    if (dst) {
+      uint64_t ticket = 0;
+      st = ss_submit_host_u8(e_, l, r, &bb, dst, bytes, &ticket);
+      if (!st) st = ss_wait_frame(e_, ticket);
+    } else {
+      st = ss_compute_host_u8(e_, l, r, &bb);
+    }
+    if (st) { py::gil_scoped_acquire gil; pool_last_ = -1; raise_status(st); }
   }
   // extension: asynchronous host frames (ss_submit_host_u8 / ss_wait_frame).  The arrays are kept alive until waited for.
   uint64_t submitHost(U8 left, U8 right, py::object out_arg, bool bbox, uint32_t x, uint32_t y, uint32_t w, uint32_t h) {
@@ -226,6 +256,7 @@ public:
     }
     ss_bbox bb{bbox ? 1 : 0, x, y, w, h};
     uint64_t ticket = 0;
+    pool_last_ = -1;
     check(ss_submit_host_u8(e_, left.data(), right.data(), &bb, dst, cap, &ticket));
     inflight_[ticket] = py::make_tuple(left, right, out_arg);
     while (inflight_.size() > 2) inflight_.erase(inflight_.begin()); // older frames were waited for inside submit
@@ -241,6 +272,7 @@ public:
   void computeCuda(py::object leftObj, py::object rightObj, bool bbox, uint32_t x, uint32_t y,
                    uint32_t w, uint32_t h, py::object stream, bool sync) {
     CudaArray left = from_object(leftObj), right = from_object(rightObj);
+    pool_last_ = -1;
     const size_t lead = lead_;
     if (left.shape.size() < 2 + lead || right.shape.size() < 2 + lead)
       throw std::runtime_error("Input image size different from initiated");
@@ -297,6 +329,10 @@ public:
       { py::gil_scoped_release nogil; st = ss_get_depth_host(e_, dst, cap); }
       check(st);
       return out;
+    }
+    if (pool_last_ >= 0) { // delivered into a pool array by the last compute(host): hand it out (a copy on repeated calls)
+      if (!pool_given_) { pool_given_ = true; return pool_[pool_last_]; }
+      return py::array_t<float>(py::array(pool_[pool_last_]).attr("copy")());
     }
     auto out = make_out({(py::ssize_t)orows_, (py::ssize_t)ocols_});
     float *dst = out.mutable_data();
@@ -428,6 +464,9 @@ private:
   size_t lead_ = 0; // 1: inputs and outputs carry a leading environment dimension (batch > 1, or batched=True)
   py::object bound_ = py::none();
   std::map<uint64_t, py::object> inflight_;
+  std::vector<py::array_t<float>> pool_; // page-locked result arrays of the strict host path
+  int pool_last_ = -1;                   // pool array that holds the last host frame (-1: none)
+  bool pool_given_ = false;
 };
 
 } // namespace

@@ -120,7 +120,7 @@ def test_banded_output_is_bit_identical(native, cfg, over):
     band = make_engine(native, prm)
     out = torch.empty((prm.rgb_rows, prm.rgb_cols), dtype=torch.float32).pin_memory().numpy()
     band.bind_output(out)
-    for seed in (1, 2, 3, 4):  # frame 1 runs stream by stream, frame 2 is captured into a CUDA graph, 3 and 4 replay it
+    for seed in (1, 2, 3, 4):  # four frames back to back (they alternate between the engine's lanes)
         left, right = configs.pair(prm, seed=seed)
         plain.compute(left, right)
         out[:] = -7.0

@@ -507,3 +507,43 @@ def test_packed_path_volumes_vs_oracle(native, oracle, over):
     batch.compute(np.stack([left, right, left]), np.stack([right, left, right]))
     assert np.array_equal(get_stage(batch, prm, "L1", index=2), ref["L1"])
     assert np.array_equal(batch.get_ndarray()[0].view(np.uint32), eng.get_ndarray().view(np.uint32))
+
+
+def test_strict_signature_results_are_never_overwritten(native):
+    """compute(l, r) + get_ndarray() with nothing else: the map is delivered into a page-locked pool array which
+    get_ndarray() hands out.  Arrays a caller keeps must stay intact however many frames follow (the pool only reuses
+    arrays nobody references; beyond four kept results it falls back to fresh arrays), repeated get_ndarray() calls
+    return equal data in distinct arrays, and writing into a returned array does not leak into later frames."""
+    prm = configs.params("small435")
+    pairs = [configs.pair(prm, seed=700 + i) for i in range(8)]
+    solo = make_engine(native, prm, lanes=1)
+    want = []
+    for l, r in pairs:
+        solo.compute(l, r)
+        want.append(solo.get_ndarray(out=np.empty((prm.rgb_rows, prm.rgb_cols), np.float32)).copy())
+    eng = make_engine(native, prm)
+    kept = []
+    for i, (l, r) in enumerate(pairs):  # keep every result: more than the pool holds
+        eng.compute(l, r)
+        a = eng.get_ndarray()
+        b = eng.get_ndarray()
+        assert a is not b and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        kept.append(a)
+        for j, k in enumerate(kept):
+            assert np.array_equal(k.view(np.uint32), want[j].view(np.uint32)), f"result {j} changed after frame {i}"
+    kept.clear()
+    for rep in range(3):  # results dropped at once: the pool arrays are reused
+        for i, (l, r) in enumerate(pairs):
+            eng.compute(l, r)
+            a = eng.get_ndarray()
+            assert np.array_equal(a.view(np.uint32), want[i].view(np.uint32))
+            a[:] = -1.0  # a caller may scribble over its own result
+    # ROI frame and device frame in between
+    eng.compute(*pairs[0], True, 8, 4, 64, 40)
+    roi = eng.get_ndarray()
+    solo.compute(*pairs[0], True, 8, 4, 64, 40)
+    assert np.array_equal(roi.view(np.uint32), solo.get_ndarray().view(np.uint32))
+    import torch
+
+    eng.compute(torch.from_numpy(pairs[3][0]).cuda(), torch.from_numpy(pairs[3][1]).cuda())
+    assert np.array_equal(eng.get_ndarray().view(np.uint32), want[3].view(np.uint32))
