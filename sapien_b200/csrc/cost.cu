@@ -284,7 +284,6 @@ __global__ void cost_generic_kernel(const uint32_t *__restrict__ cL, const uint3
   C[idx] = (uint16_t)acc;
 }
 
-static int g_cost_bpsm = 0; // experiment hook: cap on resident blocks per SM the grid is sized for (0 = occupancy)
 template <int BW, int BH, int TX, int NS, int TD, bool PACK8, int DT = 0>
 static cudaError_t launch_cfg(const uint32_t *cL, const uint32_t *cR, uint16_t *C, int N, int rows,
                               int cols, int D, cudaStream_t st) {
@@ -295,7 +294,6 @@ static cudaError_t launch_cfg(const uint32_t *cL, const uint32_t *cR, uint16_t *
   if ((e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
   int per_sm = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, TD * NS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-  if (g_cost_bpsm > 0 && per_sm > g_cost_bpsm) per_sm = g_cost_bpsm;
   const int nchunks = (D + 2 * TD - 1) / (2 * TD);
   const long xb = (long)((cols + NS * TX - 1) / (NS * TX)) * nchunks;
   // Row bands: as many as fit in ONE resident wave (a second, partial wave would double the
@@ -319,11 +317,12 @@ static cudaError_t launch_fast(const uint32_t *cL, const uint32_t *cR, uint16_t 
   // a BW-wide Hamming sum fits one byte: half-size ring (BH == 1 reads back the word it is writing)
   const bool pack8 = BH > 1 && BW * bits <= 255;
   if constexpr (BW == 7 && BH == 7) if (pack8) { // the stock block size: compile-time D for the usual disparity ranges
-    if (D == 64) return launch_cfg<BW, BH, TX, 4, 32, true, 64>(cL, cR, C, N, rows, cols, D, st);
+    // TX = 32 everywhere but D = 96: 38/32 instead of 22/16 Hamming columns per output column (C1 73.6 -> 69.5 us in
+    // round 1; C4, 256 envs: 0.530 -> 0.502 ms in round 2).  That variant uses 254 registers (2 blocks = 8 warps per SM);
+    // capping it at 168 or 128 registers for 12 / 16 warps measured 80 us and 113 us at C1: the kernel wants
+    // instruction-level parallelism, not warps.
+    if (D == 64) return launch_cfg<BW, BH, 32, 4, 32, true, 64>(cL, cR, C, N, rows, cols, D, st);
     if (D == 96) return launch_cfg<BW, BH, TX, 2, 64, true, 96>(cL, cR, C, N, rows, cols, D, st);
-    // TX = 32 at D >= 128: 38/32 instead of 22/16 Hamming columns per output column (73.6 -> 69.5 us at C1).
-    // That variant uses 254 registers (2 blocks = 8 warps per SM); capping it at 168 or 128 registers
-    // for 12 / 16 warps measured 80 us and 113 us: the kernel wants instruction-level parallelism, not warps.
     if (D == 128) return launch_cfg<BW, BH, 32, 2, 64, true, 128>(cL, cR, C, N, rows, cols, D, st);
     if (D == 256) return launch_cfg<BW, BH, 32, 2, 64, true, 256>(cL, cR, C, N, rows, cols, D, st);
   }
@@ -335,7 +334,6 @@ static cudaError_t launch_fast(const uint32_t *cL, const uint32_t *cR, uint16_t 
 }
 
 } // namespace ssb
-extern "C" int ssb_debug_set_cost_bpsm(int v) { ssb::g_cost_bpsm = v; return 0; }
 extern "C" int ssb_debug_set_cost_trace(void *device_buffer) {
   return (int)cudaMemcpyToSymbol(ssb::g_cost_trace, &device_buffer, sizeof(device_buffer));
 }
