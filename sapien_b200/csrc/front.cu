@@ -25,56 +25,59 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
   c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
 }
 struct Philox {
-  uint32_t ctr[4], key[2], out[4];
-  int have;
+  uint32_t ctr[4], key[2];
   __device__ Philox(uint64_t seed, uint64_t pixel, uint64_t frame) {
     key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32);
     ctr[0] = 0; ctr[1] = (uint32_t)frame; ctr[2] = (uint32_t)pixel; ctr[3] = (uint32_t)(pixel >> 32) ^ (uint32_t)(frame >> 32);
-    have = 0;
   }
-  __device__ uint32_t next() {
-    if (have == 0) {
-      uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
-      uint32_t k0 = key[0], k1 = key[1];
+  // one block = four 32-bit outputs; successive calls advance the counter
+  __device__ void block(uint32_t (&out)[4]) {
+    uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+    uint32_t k0 = key[0], k1 = key[1];
 #pragma unroll
-      for (int r = 0; r < 10; ++r) { philox_round(c, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
-      out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
-      ctr[0]++;
-      have = 4;
-    }
-    return out[--have];
-  }
-  __device__ float uniform() { return ((float)next() + 0.5f) * 2.3283064365386963e-10f; } // (0,1)
-  __device__ float normal() {
-    const float u1 = uniform(), u2 = uniform();
-    return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+    for (int r = 0; r < 10; ++r) { philox_round(c, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+    ctr[0]++;
   }
 };
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)x + 0.5f) * 2.3283064365386963e-10f; } // (0,1)
 
-// Marsaglia-Tsang Gamma(shape, scale), same scheme as camera.cu:21-40.
-__device__ float gamma_mt(float shape, float scale, Philox &g) {
-  float boost = 1.0f;
-  float alpha = shape;
+// IR speckle + thermal noise of one source texel (camera.cu:21-40,66-74):
+//   round(I * Gamma(shape, scale) + mu + sigma * N(0,1)), clamped to [0,255],
+// Gamma by Marsaglia-Tsang exactly as the reference (boost by u^(1/shape) for shape < 1).  One Philox block serves
+// the common case: its first two outputs give BOTH Box-Muller normals (the cosine one proposes the Gamma variate, the
+// sine one is the thermal noise -- the two are independent), the third the acceptance uniform; only a rejected proposal
+// (~2 % at the stock shape) or shape < 1 draws further blocks.  The acceptance test is the reference's, preceded by
+// Marsaglia-Tsang's squeeze (u < 1 - 0.0331 z^4 implies acceptance), which skips both logarithms most of the time
+// without changing a single decision.
+__device__ __noinline__ int ir_noise(const FrontParams &p, int v, size_t sp, int which) {
+  Philox g(p.seed + (uint64_t)which, (uint64_t)sp, p.frame);
+  uint32_t r[4];
+  g.block(r);
+  float rad = sqrtf(-2.0f * logf(u01(r[0])));
+  float sn, cs;
+  sincospif(2.0f * u01(r[1]), &sn, &cs);
+  const float thermal = rad * sn;
+  float z = rad * cs, u = u01(r[2]);
+  float boost = 1.0f, alpha = p.speckle_shape;
   if (alpha < 1.0f) {
-    boost = powf(g.uniform(), 1.0f / alpha);
+    boost = powf(u01(r[3]), 1.0f / alpha);
     alpha += 1.0f;
   }
   const float d = alpha - 1.0f / 3.0f, c = rsqrtf(9.0f * d);
+  float gam = d; // (after 64 rejections in a row -- probability ~1e-100 -- the mode)
   for (int it = 0; it < 64; ++it) {
-    const float z = g.normal(), u = g.uniform();
     const float t = 1.0f + c * z;
-    const float v = t * t * t;
-    if (t > 0.0f && logf(u) < 0.5f * z * z + d - d * v + d * logf(v)) return d * v * scale * boost;
+    const float w = t * t * t;
+    const float z2 = z * z;
+    if (t > 0.0f && (u < 1.0f - 0.0331f * z2 * z2 || logf(u) < 0.5f * z2 + d - d * w + d * logf(w))) { gam = d * w; break; }
+    g.block(r);
+    rad = sqrtf(-2.0f * logf(u01(r[0])));
+    z = rad * cospif(2.0f * u01(r[1]));
+    u = u01(r[2]);
   }
-  return d * scale * boost;
-}
-
-// IR speckle + thermal noise of one source texel (camera.cu:66-74)
-__device__ __noinline__ int ir_noise(const FrontParams &p, int v, size_t sp, int which) {
-  Philox g(p.seed + (uint64_t)which, (uint64_t)sp, p.frame);
-  const float r = roundf((float)v * gamma_mt(p.speckle_shape, p.speckle_scale, g) + p.gaussian_mu +
-                         p.gaussian_sigma * g.normal());
-  return min(max((int)r, 0), 255);
+  const float res = roundf((float)v * (gam * p.speckle_scale * boost) + p.gaussian_mu + p.gaussian_sigma * thermal);
+  return min(max((int)res, 0), 255);
 }
 
 // noise stream id of a texel = its PACKED pixel index inside the environment, whatever the source pitch
