@@ -498,7 +498,7 @@ def run_ours(args, rank, world, local):
     out_shape = ((batch,) if batch > 1 else ()) + (prm.rgb_rows, prm.rgb_cols)
     pin_out = torch.empty(out_shape, dtype=torch.float32).pin_memory()
     out_np = pin_out.numpy()
-    e2e_steps = max(3, min(args.steps, 30))
+    e2e_steps = max(60, min(args.steps, 200))  # (its own step count: 20 frames would mostly time the fill and drain of the pipeline)
 
     def e2e_loop(fn):
         for i in range(3):
@@ -661,7 +661,7 @@ def run_reference(args, rank, world, local):
     barrier(world)
     ms = max_over_ranks(e0.elapsed_time(e1), world)
     value = batch * steps * world / (ms / 1e3)
-    e2e_steps = max(3, min(steps, 20))
+    e2e_steps = max(20, min(steps, 60))
     out = None
     for i in range(2):
         ref.compute_host(*host_sets[i % n_sets], bbox_t)
