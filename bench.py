@@ -457,7 +457,7 @@ def run_ours(args, rank, world, local):
         l, r = dev_sets[i % n_sets]
         eng.compute(l, r, *bb, stream=own, sync=False)
         if pc:
-            eng.get_rgb_point_cloud_cuda(rgba)
+            eng.get_rgb_point_cloud_cuda(rgba, sync=False)  # stream-ordered: the kernel follows the frame on its lane
 
     torch.cuda.synchronize()
     sampler = ClockSampler(local)  # 100 ms samples from the warm-up to the end of the batched block (each timed region is short)

@@ -189,6 +189,11 @@ int ss_get_rgb_point_cloud_host(ss_engine *e, const void *rgba_device, float *ou
 /* E:70 getRgbPointCloudCudaPtr / P:130-139 */
 int ss_get_rgb_point_cloud_device(ss_engine *e, const void *rgba_device, void **ptr);
 
+/* Extension: the point cloud of the last frame WITHOUT a host synchronisation (the reference's device getters block,
+ * C:409-411, 452): the kernel is enqueued behind the frame and *ptr is valid for work ordered on the engine's public
+ * stream (ss_get_stream) after this call.  rgba_device = NULL: xyz [..][3]; else xyz + rgb [..][6]. */
+int ss_enqueue_point_cloud(ss_engine *e, const void *rgba_device, void **ptr);
+
 /* E:73-79 / C:457-482.  Validated against the ranges of
  * python/py_package/sensor/simsense_component.py:54-134; take effect at the next compute. */
 int ss_set_ir_noise_parameters(ss_engine *e, float speckle_shape, float speckle_scale,

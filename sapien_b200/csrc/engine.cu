@@ -900,6 +900,16 @@ static int core_get_point_cloud_device(Core *e, void **ptr) {
   *ptr = e->pc;
   return SS_OK;
 }
+// stream-ordered variants: the kernel is enqueued behind the frame, nothing waits on the host
+static int core_enqueue_point_cloud(Core *e, const void *rgba, void **ptr) {
+  if (!e || !ptr) return fail(SS_ERR_INVALID, "null argument");
+  if (!e->computed) return fail(SS_ERR_NOT_COMPUTED, "No computed data stored");
+  DeviceGuard g(e->device);
+  int r = run_pc(e, rgba);
+  if (r) return r;
+  *ptr = rgba ? e->rgbpc : e->pc;
+  return SS_OK;
+}
 static int core_get_rgb_point_cloud_host(Core *e, const void *rgba, float *out, size_t cap) {
   if (!e || !rgba) return fail(SS_ERR_INVALID, "null argument");
   if (!e->computed) return fail(SS_ERR_NOT_COMPUTED, "No computed data stored");
@@ -1235,6 +1245,16 @@ int ss_get_rgb_point_cloud_host(ss_engine *e, const void *rgba, float *out, size
 int ss_get_rgb_point_cloud_device(ss_engine *e, const void *rgba, void **ptr) { SS_LAST(core_get_rgb_point_cloud_device, rgba, ptr) }
 int ss_get_stage_host(ss_engine *e, const char *name, int32_t index, void *out, size_t cap, size_t *bytes) {
   SS_LAST(core_get_stage_host, name, index, out, cap, bytes)
+}
+int ss_enqueue_point_cloud(ss_engine *e, const void *rgba_device, void **ptr) {
+  if (!e) return fail(SS_ERR_INVALID, "null engine");
+  Core *c = e->lane[e->last];
+  int r = core_enqueue_point_cloud(c, rgba_device, ptr);
+  if (r) return r;
+  DeviceGuard g(e->device); // the public stream completes behind the point-cloud kernel as well
+  CK(cudaEventRecord(e->ev_join, c->stream));
+  CK(cudaStreamWaitEvent(e->pub, e->ev_join, 0));
+  return SS_OK;
 }
 int ss_get_launches_per_compute(ss_engine *e, int32_t *count) { SS_LAST(core_get_launches_per_compute, count) }
 

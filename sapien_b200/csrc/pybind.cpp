@@ -362,9 +362,9 @@ public:
     check(ss_get_point_cloud_host(e_, out.mutable_data(), (size_t)out.nbytes()));
     return out;
   }
-  CudaArray getPointCloudCuda() {
+  CudaArray getPointCloudCuda(bool sync) {
     void *p = nullptr;
-    check(ss_get_point_cloud_device(e_, &p));
+    check(sync ? ss_get_point_cloud_device(e_, &p) : ss_enqueue_point_cloud(e_, nullptr, &p));
     return view(p, {(int64_t)orows_ * ocols_, 3});
   }
   py::array_t<float> getRgbPointCloudNdarray(py::object rgba) {
@@ -373,10 +373,10 @@ public:
     check(ss_get_rgb_point_cloud_host(e_, a.ptr, out.mutable_data(), (size_t)out.nbytes()));
     return out;
   }
-  CudaArray getRgbPointCloudCuda(py::object rgba) {
+  CudaArray getRgbPointCloudCuda(py::object rgba, bool sync) {
     CudaArray a = checkedRgba(rgba);
     void *p = nullptr;
-    check(ss_get_rgb_point_cloud_device(e_, a.ptr, &p));
+    check(sync ? ss_get_rgb_point_cloud_device(e_, a.ptr, &p) : ss_enqueue_point_cloud(e_, a.ptr, &p));
     return view(p, {(int64_t)orows_ * ocols_, 6});
   }
 
@@ -533,10 +533,10 @@ PYBIND11_MODULE(_simsense_b200, m) {
       .def("get_ndarray", &E::getNdarray, "out"_a = py::none())
       .def("bind_output", &E::bindOutput, "out"_a)
       .def("get_cuda", &E::getCuda)
-      .def("get_point_cloud_cuda", &E::getPointCloudCuda)
+      .def("get_point_cloud_cuda", &E::getPointCloudCuda, "sync"_a = true)
       .def("get_point_cloud_ndarray", &E::getPointCloudNdarray)
       .def("get_rgb_point_cloud_ndarray", &E::getRgbPointCloudNdarray)
-      .def("get_rgb_point_cloud_cuda", &E::getRgbPointCloudCuda)
+      .def("get_rgb_point_cloud_cuda", &E::getRgbPointCloudCuda, "rgba_cuda"_a, "sync"_a = true)
       .def("set_ir_noise_parameters", &E::setIrNoise)
       .def("set_census_window_size", &E::setCensus)
       .def("set_matching_block_size", &E::setBlock)
