@@ -577,3 +577,27 @@ def test_stream_ordered_point_clouds(native, oracle):
         np.testing.assert_allclose(snaps[i].cpu().numpy(), want, rtol=1e-4, atol=1e-6)
         ref = oracle.pipeline(prm, *pairs[i], volumes=False)
         assert_depth_close(depths[i].cpu().numpy(), ref["out"])
+
+
+def test_invalid_pixels_that_splat_inside_the_image(native, oracle):
+    """b3 > 0 with (b1/b3, b2/b3) inside the RGB image: every invalid disparity (z = 0) splats zRgb = b3 onto that one
+    pixel (camera.cu:187-195 does not skip z = 0).  The banded host delivery assumes an RGB column is final once the
+    matched columns that can reach it are done -- not true for that pixel -- so it must switch itself off: bound
+    output, plain read-back and the oracle agree."""
+    import torch
+
+    prm = variant(configs.params("small435"), b1=60.0, b2=40.0, b3=1.0)
+    left, right = configs.pair(prm, seed=900)
+    ref = oracle.pipeline(prm, left, right, volumes=False)
+    assert ref["out"][40, 60] == np.float32(1.0)  # the pixel all invalid disparities land on
+    plain = make_engine(native, prm)
+    plain.compute(left, right)
+    assert_depth_close(plain.get_ndarray(), ref["out"])
+    band = make_engine(native, prm)
+    out = torch.empty((prm.rgb_rows, prm.rgb_cols), dtype=torch.float32).pin_memory().numpy()
+    band.bind_output(out)
+    for _ in range(3):
+        out[:] = -1.0
+        band.compute(left, right)
+        band.get_ndarray(out=out)
+        assert np.array_equal(out.view(np.uint32), plain.get_ndarray().view(np.uint32))
