@@ -25,6 +25,11 @@ namespace {
 
 thread_local std::string g_err;
 
+// debug hooks (not part of include/ss_b200.h): 0 turns the 12-bit storage of the path volumes off (A/B measurements);
+// a cap on the environments per wave makes engines created afterwards run their batches in several waves (tests)
+int g_allow_pack12 = 1;
+int g_max_wave = 0;
+
 int fail(int code, const std::string &msg) {
   g_err = msg;
   return code;
@@ -262,6 +267,7 @@ int create_impl(Core *e, const float *mapLx, const float *mapLy, const float *ma
   if (free_b < small + (size_t)nvol * vol) return fail(SS_ERR_CUDA, "not enough device memory for one frame");
   size_t budget = (size_t)((double)(free_b - small) * 0.6);
   e->wave = (int)std::min<size_t>(N, std::max<size_t>(1, budget / ((size_t)nvol * vol)));
+  if (g_max_wave > 0) e->wave = std::min(e->wave, g_max_wave); // (test hook: exercise the multi-wave path on a big GPU)
   const size_t wv = (size_t)e->wave * fsz * c.max_disp;
   if ((r = e->alloc(&e->C, wv))) return r;
   if ((r = e->alloc(&e->L1, wv))) return r;
@@ -295,8 +301,7 @@ int create_impl(Core *e, const float *mapLx, const float *mapLy, const float *ma
 
 enum InputKind { IN_U8, IN_RGBA };
 
-// debug hook (not part of include/ss_b200.h): 0 turns the 12-bit storage of the path volumes off (A/B measurements)
-int g_allow_pack12 = 1;
+
 
 // host_left / host_right: when non-null (host-u8 path, one wave, 7x7 census) the uploads happen here,
 // the right image on the helper stream, so that the left image's front-end overlaps the second upload
@@ -596,6 +601,7 @@ int compute_impl(Core *e, InputKind kind, const void *left, const void *right,
 } // namespace
 
 extern "C" int ssb_debug_set_pack12(int on) { g_allow_pack12 = on; return 0; }
+extern "C" int ssb_debug_set_max_wave(int n) { g_max_wave = n; return 0; }
 
 // Host-facing calls that read results through the main stream first join whatever an asynchronous frame left on the
 // helper and copy streams (its column bands and their copies).

@@ -149,6 +149,19 @@ def test_sensor_facade_on_gpu(native, oracle):
     with pytest.raises(TypeError):
         sensor.set_penalties(60, 4)
     assert sensor.get_config().p1_penalty == 4
+    # the STOCK configuration (D435, IR noise on: speckle 1.0, thermal 1.0) runs and stays close to the noise-free result
+    stock = StereoDepthSensor(StereoDepthSensorConfig())
+    p435 = configs.params("C3")
+    l4, r4 = configs.pair(variant(p435, max_disp=128), seed=6)
+    stock.set_pictures(l4, r4)
+    stock.compute_depth()
+    noisy = stock.get_depth()
+    stock.set_ir_noise(0.0, 0.0)
+    stock.compute_depth()
+    clean = stock.get_depth()
+    assert noisy.shape == clean.shape == (480, 848)
+    both = (noisy > 0) & (clean > 0)
+    assert both.mean() > 0.5 * (clean > 0).mean() and np.median(np.abs(noisy[both] - clean[both]) / clean[both]) < 0.02
 
 
 def test_raw_c_abi_compute_through_ctypes(native, oracle):
@@ -601,3 +614,39 @@ def test_invalid_pixels_that_splat_inside_the_image(native, oracle):
         band.compute(left, right)
         band.get_ndarray(out=out)
         assert np.array_equal(out.view(np.uint32), plain.get_ndarray().view(np.uint32))
+
+
+@pytest.mark.parametrize("cfg,batch,wave", [("C4", 5, 2), ("small435", 7, 3), ("small", 3, 1)])
+def test_batches_larger_than_one_wave(native, oracle, cfg, batch, wave):
+    """A batch that does not fit the memory budget runs in waves of `wave` environments (front-end, cost volume and the
+    four passes per wave on the same volumes, post-processing once for the whole batch).  On a 180 GB GPU that never
+    happens by itself: a debug hook caps the wave size.  Device-RGBA, host and pipelined host inputs."""
+    import ctypes
+    import torch
+
+    from tests.test_cabi_cpu import LIB
+
+    lib = ctypes.CDLL(LIB)
+    prm = configs.params(cfg)
+    pairs = [configs.pair(prm, seed=950 + i) for i in range(batch)]
+    l, r = np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs])
+    whole = make_engine(native, prm, batch=batch)
+    whole.compute(l, r)
+    want = whole.get_ndarray().copy()
+    ref = oracle.pipeline(prm, *pairs[batch - 1], volumes=False)
+    assert_depth_close(want[batch - 1], ref["out"])
+    lib.ssb_debug_set_max_wave(wave)
+    try:
+        eng = make_engine(native, prm, batch=batch)
+    finally:
+        lib.ssb_debug_set_max_wave(0)
+    for _ in range(2):
+        eng.compute(l, r)
+        assert np.array_equal(eng.get_ndarray().view(np.uint32), want.view(np.uint32))
+        eng.compute(torch.from_numpy(synth.to_rgba(l)).cuda(), torch.from_numpy(synth.to_rgba(r)).cuda())
+        assert np.array_equal(eng.get_cuda().torch().cpu().numpy().view(np.uint32), want.view(np.uint32))
+    out = torch.empty((batch, prm.rgb_rows, prm.rgb_cols), dtype=torch.float32).pin_memory().numpy()
+    t = eng.submit(l, r, out=out)
+    eng.wait(t)
+    assert np.array_equal(out.view(np.uint32), want.view(np.uint32))
+    assert_stages_equal(eng, prm, ref, names=("census0", "disp_wta", "disp_right", "disp_med", "depth"), index=batch - 1)
