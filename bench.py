@@ -598,6 +598,8 @@ def run_ours(args, rank, world, local):
         "dtype": "u16", "data": "synthetic",
         "config": shared_config(args, desc, batch, world),
         "arm": {"impl": "sapien_b200 (this repo)", "volumes_mb": 4 * V / 1e6, "lanes": eng_lanes, "host_enqueue_us_per_frame": host_us,
+                "one_lane": {"ms_per_step": sum(st_ms.values()), "value": batch * 1e3 / max(sum(st_ms.values()), 1e-9),
+                             "note": "the same frames on ONE lane (the profiled loop: sum of the stage times), i.e. without the overlap of consecutive frames"},
                 "pipelining": "frames enqueued back to back; consecutive frames alternate between the engine's lanes (independent stream / buffer sets) and overlap on the GPU, "
                               "results in submission order on the engine's public stream; the front-end of a frame runs under the previous frame of its lane"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches * args.steps,

@@ -107,7 +107,7 @@ struct Core {
   // banded output (ss_bind_output_host): the final SGM pass runs in column segments and the depth map
   // streams to the bound host buffer band by band while the remaining segments compute
   static constexpr int MAXSEG = 6;
-  cudaEvent_t ev_seg[MAXSEG] = {}, ev_band[MAXSEG] = {}, ev_copied = nullptr;
+  cudaEvent_t ev_seg[MAXSEG] = {}, ev_band[MAXSEG] = {};
   float *host_out = nullptr;    // caller-bound output (ss_bind_output_host)
   size_t host_cap = 0;
   float *staging = nullptr;     // engine-owned pinned output of host-input frames when nothing is bound (the
@@ -208,7 +208,6 @@ int create_impl(Core *e, const float *mapLx, const float *mapLy, const float *ma
   for (auto &ev : e->ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto &ev : e->ev_seg) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto &ev : e->ev_band) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  CK(cudaEventCreateWithFlags(&e->ev_copied, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&e->ev_cost, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&e->ev_front, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
@@ -673,16 +672,14 @@ static int create_common(const ss_config *cfg, const ss_calibration *cal, const 
 static int core_destroy(Core *e) {
   if (!e) return SS_OK;
   DeviceGuard g(e->device);
-  if (e->stream) cudaStreamSynchronize(e->stream);
-  if (e->aux) cudaStreamSynchronize(e->aux);
-  if (e->cpy) cudaStreamSynchronize(e->cpy);
+  for (cudaStream_t s : {e->stream, e->aux, e->cpy, e->up, e->fr})
+    if (s) cudaStreamSynchronize(s);
   for (void *p : e->allocs) cudaFree(p);
   if (e->staging) cudaFreeHost(e->staging);
   for (auto ev : e->pev) cudaEventDestroy(ev);
   for (auto ev : e->ev) if (ev) cudaEventDestroy(ev);
   for (auto ev : e->ev_seg) if (ev) cudaEventDestroy(ev);
   for (auto ev : e->ev_band) if (ev) cudaEventDestroy(ev);
-  if (e->ev_copied) cudaEventDestroy(e->ev_copied);
   for (cudaEvent_t ev : {e->ev_upL, e->ev_upR, e->ev_lastband[0], e->ev_lastband[1], e->ev_rawfree[0], e->ev_rawfree[1], e->ev_done[0], e->ev_done[1]})
     if (ev) cudaEventDestroy(ev);
   if (e->up) { cudaStreamSynchronize(e->up); cudaStreamDestroy(e->up); }
