@@ -279,8 +279,10 @@ cudaError_t launch_post(const PostParams &p_in, cudaStream_t st, int *launches) 
     ++nl;
   }
   if (p.registration && p.ub > p.ua) {
-    const dim3 dg((unsigned)((p.ub - p.ua + 4 * 128 - 1) / (4 * 128)), (unsigned)p.rgb_rows, (unsigned)p.N);
-    dilate_range_kernel<<<dg, 128, 0, st>>>(p);
+    const int span = p.ub - p.ua; // 4 pixels per thread; narrow images / bands get narrower blocks instead of idle warps
+    const int threads = span <= 128 ? 32 : (span <= 256 ? 64 : 128);
+    const dim3 dg((unsigned)((span + 4 * threads - 1) / (4 * threads)), (unsigned)p.rgb_rows, (unsigned)p.N);
+    dilate_range_kernel<<<dg, threads, 0, st>>>(p);
     ++nl;
   }
   if (launches) *launches = nl;
