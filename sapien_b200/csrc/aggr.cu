@@ -206,14 +206,23 @@ template <int NR> __device__ __forceinline__ void st_pack12(unsigned char *piece
 // selUp / selDn are per-lane PRMT selectors: 0x5432 = take the neighbour lane's half, 0x5454 /
 // 0x3232 (first / last disparity) = repeat the own value, which makes the missing neighbour
 // harmless (L(d)+P1 never beats L(d)).  L == 0 everywhere reproduces the first-pixel rule L = C.
-template <int NR>
+// Minimum over the 16 lanes of the caller's half-warp, for both halves at once (two row paths share a warp, see
+// aggr_wta2_kernel): CREDUX reduces the whole warp into a uniform register, so each half takes its turn with the
+// other half contributing the neutral element.
+__device__ __forceinline__ uint32_t halfwarp_min(uint32_t t, bool upper) {
+  const uint32_t lo = __reduce_min_sync(FULL, upper ? 0xffffffffu : t);
+  const uint32_t hi = __reduce_min_sync(FULL, upper ? t : 0xffffffffu);
+  return upper ? hi : lo;
+}
+
+template <int NR, bool HALF = false>
 __device__ __forceinline__ void sgm_step(uint32_t (&L)[NR], const uint32_t (&c)[NR], uint32_t P1P1,
-                                         uint32_t P2P2, uint32_t selUp, uint32_t selDn) {
+                                         uint32_t P2P2, uint32_t selUp, uint32_t selDn, bool upper = false) {
   uint32_t t = L[0];
 #pragma unroll
   for (int j = 1; j < NR; ++j) t = __vminu2(t, L[j]);
   t = __vminu2(t, __byte_perm(t, t, 0x1032));        // both halves = lane minimum
-  const uint32_t mm = __reduce_min_sync(FULL, t);     // m | m << 16
+  const uint32_t mm = HALF ? halfwarp_min(t, upper) : __reduce_min_sync(FULL, t); // m | m << 16
   const uint32_t mP2 = mm + P2P2;
   const uint32_t up = __shfl_up_sync(FULL, L[NR - 1], 1);
   const uint32_t dn = __shfl_down_sync(FULL, L[0], 1);
@@ -458,6 +467,56 @@ __global__ void __launch_bounds__(128) aggr_kernel(const __grid_constant__ AggrA
   if (tr && lane == 0) tr[4 * tslot + 1] = gtimer();
 }
 
+// Uniqueness test + sub-pixel interpolation of ONE pixel by one lane (wta.cu:164-168,203): `row` = the pixel's D
+// blended costs in shared memory (the d*-1..d*+1 window is overwritten), gk = min << 16 | argmin.
+__device__ __forceinline__ float wta_pixel(uint16_t *row, uint32_t gk, int D, int k100u) {
+  const int m = (int)(gk >> 16), ds = (int)(gk & 0xffffu);
+  int y0 = 0, y2 = 0;
+  if (ds > 0) y0 = row[ds - 1];
+  if (ds < D - 1) y2 = row[ds + 1];
+  bool ok;
+  if (k100u > 0) {
+    // unique <=> min over d outside [d*-1, d*+1] of LAll(d)*(100-u) >= m*100 (wta.cu:203)
+    if (ds > 0) row[ds - 1] = 0xffffu;
+    row[ds] = 0xffffu;
+    if (ds < D - 1) row[ds + 1] = 0xffffu;
+    uint32_t mn0 = 0xffffffffu, mn1 = 0xffffffffu, mn2 = 0xffffffffu, mn3 = 0xffffffffu;
+    const uint4 *r4 = reinterpret_cast<const uint4 *>(row);
+    int i = 0;
+    for (; i + 4 <= D / 8; i += 4) { // 4 independent chains: the loads of one round overlap
+      const uint4 v0 = r4[i], v1 = r4[i + 1], v2 = r4[i + 2], v3 = r4[i + 3];
+      mn0 = __vimin3_u16x2(mn0, v0.x, v0.y); mn1 = __vimin3_u16x2(mn1, v1.x, v1.y);
+      mn2 = __vimin3_u16x2(mn2, v2.x, v2.y); mn3 = __vimin3_u16x2(mn3, v3.x, v3.y);
+      mn0 = __vimin3_u16x2(mn0, v0.z, v0.w); mn1 = __vimin3_u16x2(mn1, v1.z, v1.w);
+      mn2 = __vimin3_u16x2(mn2, v2.z, v2.w); mn3 = __vimin3_u16x2(mn3, v3.z, v3.w);
+    }
+    for (; i < D / 8; ++i) {
+      const uint4 v = r4[i];
+      mn0 = __vimin3_u16x2(mn0, v.x, v.y);
+      mn1 = __vimin3_u16x2(mn1, v.z, v.w);
+    }
+    const uint32_t mn = __vimin3_u16x2(mn0, mn1, __vminu2(mn2, mn3));
+    const int m2 = (int)min(mn & 0xffffu, mn >> 16);
+    ok = m2 * k100u >= m * 100;
+  } else { // uniqueness_ratio >= 100: the product test is not monotone; evaluate it literally
+    ok = true;
+    for (int d = 0; d < D; ++d) {
+      const int dd = d - ds;
+      ok = ok && ((int)row[d] * k100u >= m * 100 || (dd >= -1 && dd <= 1));
+    }
+  }
+  float disp = (float)ds;
+  if (!ok) {
+    disp = -1.0f;
+  } else if (ds != 0 && ds != D - 1) {
+    // wta.cu:164-168 computes (double)(y2-y0) / (2.0*(double)(y0-2*y1+y2)) and rounds to float.
+    // Numerator and denominator are integers < 2^20, so ONE correctly rounded float division
+    // gives the same bits (no double-rounding case exists for |num|,den < 2^24).
+    disp = (float)ds - __fdiv_rn((float)(y2 - y0), (float)(2 * (y0 - 2 * m + y2)));
+  }
+  return disp;
+}
+
 // ---- MODE 2: left->right path + blend + winner-takes-all, two warps per image row ---------------
 // Warp 0 (producer) walks the path: SGM step, LAll = (L0 + S3)/4, row -> shared tile.  Warp 1
 // (consumer) follows one tile (32 pixels) behind: packed (min,argmin) keys, the right-disparity
@@ -639,52 +698,7 @@ __global__ void __launch_bounds__(512, 1) aggr_wta_kernel(const __grid_constant_
   auto tile_phase = [&](unsigned char *tbase, int t0, int cnt) {
     __syncwarp();
     if (lane < cnt) {
-      const uint32_t gk = gkbuf[lane];
-      const int m = (int)(gk >> 16), ds = (int)(gk & 0xffffu);
-      uint16_t *row = reinterpret_cast<uint16_t *>(tbase + lane * TP);
-      int y0 = 0, y2 = 0;
-      if (ds > 0) y0 = row[ds - 1];
-      if (ds < D - 1) y2 = row[ds + 1];
-      bool ok;
-      if (k100u > 0) {
-        // unique <=> min over d outside [d*-1, d*+1] of LAll(d)*(100-u) >= m*100 (wta.cu:203)
-        if (ds > 0) row[ds - 1] = 0xffffu;
-        row[ds] = 0xffffu;
-        if (ds < D - 1) row[ds + 1] = 0xffffu;
-        uint32_t mn0 = 0xffffffffu, mn1 = 0xffffffffu, mn2 = 0xffffffffu, mn3 = 0xffffffffu;
-        const uint4 *r4 = reinterpret_cast<const uint4 *>(row);
-        int i = 0;
-        for (; i + 4 <= D / 8; i += 4) { // 4 independent chains: the loads of one round overlap
-          const uint4 v0 = r4[i], v1 = r4[i + 1], v2 = r4[i + 2], v3 = r4[i + 3];
-          mn0 = __vimin3_u16x2(mn0, v0.x, v0.y); mn1 = __vimin3_u16x2(mn1, v1.x, v1.y);
-          mn2 = __vimin3_u16x2(mn2, v2.x, v2.y); mn3 = __vimin3_u16x2(mn3, v3.x, v3.y);
-          mn0 = __vimin3_u16x2(mn0, v0.z, v0.w); mn1 = __vimin3_u16x2(mn1, v1.z, v1.w);
-          mn2 = __vimin3_u16x2(mn2, v2.z, v2.w); mn3 = __vimin3_u16x2(mn3, v3.z, v3.w);
-        }
-        for (; i < D / 8; ++i) {
-          const uint4 v = r4[i];
-          mn0 = __vimin3_u16x2(mn0, v.x, v.y);
-          mn1 = __vimin3_u16x2(mn1, v.z, v.w);
-        }
-        const uint32_t mn = __vimin3_u16x2(mn0, mn1, __vminu2(mn2, mn3));
-        const int m2 = (int)min(mn & 0xffffu, mn >> 16);
-        ok = m2 * k100u >= m * 100;
-      } else { // uniqueness_ratio >= 100: the product test is not monotone; evaluate it literally
-        ok = true;
-        for (int d = 0; d < D; ++d) {
-          const int dd = d - ds;
-          ok = ok && ((int)row[d] * k100u >= m * 100 || (dd >= -1 && dd <= 1));
-        }
-      }
-      float disp = (float)ds;
-      if (!ok) {
-        disp = -1.0f;
-      } else if (ds != 0 && ds != D - 1) {
-        // wta.cu:164-168 computes (double)(y2-y0) / (2.0*(double)(y0-2*y1+y2)) and rounds to float.
-        // Numerator and denominator are integers < 2^20, so ONE correctly rounded float division
-        // gives the same bits (no double-rounding case exists for |num|,den < 2^24).
-        disp = (float)ds - __fdiv_rn((float)(y2 - y0), (float)(2 * (y0 - 2 * m + y2)));
-      }
+      const float disp = wta_pixel(reinterpret_cast<uint16_t *>(tbase + lane * TP), gkbuf[lane], D, k100u);
       a.dispL[rowpix + t0 + lane] = disp;
       const int xr = t0 + lane - (D - 1);
       if (xr >= 0) a.dispR[rowpix + xr] = rbuf[lane];
@@ -742,6 +756,245 @@ __global__ void __launch_bounds__(512, 1) aggr_wta_kernel(const __grid_constant_
   if (tr && lane == 0) tr[4 * tslot + 3] = gtimer();
 }
 
+// ---- MODE 2, two rows per warp pair (whole power-of-two disparity ranges, production build) -----------------------
+// Same algorithm and hand-over as aggr_wta_kernel, but a row path occupies a HALF-warp: lane = (h, l), h = lane >> 4
+// picks one of two adjacent image rows, the 16 lanes l own 2*NR = D/16 consecutive disparities each.  What this buys:
+//  * every per-step instruction that does not scale with NR (reduction, shuffles, border selectors, barrier / ring
+//    bookkeeping, the consumer's key minimum and stores) is shared by two pixels -- at D = 64 a step of the one-row
+//    kernel costs 19 + 19 warp instructions per pixel (producer + consumer), which is what bounds the batched
+//    low-resolution workload (BASELINE C4), not HBM;
+//  * half as many producer / consumer warps for the same rows: 720 rows are 360 pairs, i.e. at most 3 producer and
+//    3 consumer warps per SM instead of 5 + 5 on 4 schedulers, so the serial chain that bounds a single frame shares
+//    its scheduler with less.
+// The per-half minimum is two CREDUX (halfwarp_min); the shuffles stay full-warp, the lanes at the half borders
+// ignore what they receive through the same PRMT selectors that implement the d = 0 / d = D-1 rule.
+// A tile is 16 steps x 2 rows = 32 pixels, so the one-lane-per-pixel phase is unchanged.
+constexpr int W2_TS = 16; // steps per tile
+template <int K, int NCH> __host__ __device__ inline AggrSmem aggr2_smem(int D) {
+  AggrSmem s;
+  const int piece = D * 2;
+  s.ring = 128; // mbarriers: NCH bulk-copy barriers, then WTA_TILES full + WTA_TILES empty
+  s.tile = s.ring + 2 /*streams*/ * NCH * 2 /*rows*/ * K * piece;
+  s.gk = s.tile + (WTA_TILES * 32 + 1) * (piece + 16);
+  s.rb = s.gk + 32 * 4;
+  s.total = s.rb + 32 * 2;
+  s.total = (s.total + 127) & ~127;
+  return s;
+}
+
+template <int NR, int K, int NCH>
+__global__ void __launch_bounds__(NR >= 8 ? 256 : 512, 1) aggr_wta2_kernel(const __grid_constant__ AggrArgs a) {
+  static_assert(W2_TS % K == 0, "a tile is a whole number of chunks");
+  constexpr int DPL = 2 * NR;
+  constexpr int D = 32 * NR;
+  constexpr int PIECE = D * 2;
+  constexpr int TP = PIECE + 16;       // tile row pitch: the per-pixel phase's lanes hit distinct banks
+  constexpr int ROWCH = K * PIECE;     // bytes of one row's chunk
+  constexpr int STREAM = NCH * 2 * ROWCH;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int h = lane >> 4, l = lane & 15;
+  const bool upper = h != 0;
+  // Roles.  ppb pairs per block: producers on warps 0..ppb-1; with three pairs (the single-frame regime: one block
+  // per SM) the consumers take warps 3, 4, 5, i.e. schedulers 3, 0, 1 -- one consumer has a scheduler to itself, two
+  // share with a producer, one producer runs alone.
+  const int ppb = blockDim.x >> 6;
+  const int role = warp >= ppb;
+  const int pi = role ? warp - ppb : warp;
+  const long npaths = (long)a.N * a.rows;
+  const long pair = (long)blockIdx.x * ppb + pi;
+  const bool valid = 2 * pair < npaths;
+  const AggrSmem lay = aggr2_smem<K, NCH>(D);
+  unsigned char *wsm = smem_raw + (size_t)pi * lay.total;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(wsm);
+  const uint32_t barFull = bar0 + 8 * NCH, barEmpty = barFull + 8 * WTA_TILES;
+  if (role == 0 && lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NCH + 2 * WTA_TILES; ++i) mbar_init(bar0 + 8 * i, i < NCH ? 1 : 32); // tile hand-over: every lane arrives
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads(); // the only block-level barrier: mbarriers are initialised
+  if (!valid) return;
+  const long mypath = 2 * pair + h;
+  const bool rowvalid = mypath < npaths;              // an odd number of rows: the last pair's upper half repeats the last row
+  const PathGeom pg = path_geom(a, rowvalid ? mypath : npaths - 1);
+  const int steps = pg.steps; // == cols
+  const int loff = l * NR * 4;
+  unsigned char *tile = wsm + lay.tile;
+  const int ntiles = (steps + W2_TS - 1) / W2_TS;
+  unsigned long long *const tr = g_trace;
+  const int tslot = 3 * TRACE_STRIDE + (int)((2 * pair) % TRACE_STRIDE);
+  if (tr && lane == 0 && role == 0) { tr[4 * tslot] = gtimer(); tr[4 * tslot + 2] = smid(); }
+
+  if (role == 0) {
+    // =========================== producer: two SGM paths + blend ==============================
+    const uint32_t ring_s = bar0 + lay.ring;
+    const unsigned char *ring = wsm + lay.ring;
+    // lane 0 issues the copies of both rows: it needs the other row's base as well
+    const PathGeom pgB = path_geom(a, 2 * pair + 1 < npaths ? 2 * pair + 1 : npaths - 1);
+    const char *gC[2] = {reinterpret_cast<const char *>(a.C + pg.e0), reinterpret_cast<const char *>(a.C + pgB.e0)};
+    const char *gS[2] = {reinterpret_cast<const char *>(a.aux0 + pg.e0), reinterpret_cast<const char *>(a.aux0 + pgB.e0)};
+    const int nchunks = (steps + K - 1) / K;
+    auto issue = [&](int ci) { // chunk ci -> slot ci % NCH: 2 streams x 2 rows, one bulk copy each
+      if (lane != 0) return;
+      const int slot = ci % NCH;
+      const int s0 = ci * K;
+      const int kc = min(K, steps - s0);
+      const uint32_t bar = bar0 + 8 * slot;
+      const uint32_t dst = ring_s + (uint32_t)(slot * 2 * ROWCH);
+      mbar_expect_tx(bar, (uint32_t)(4 * kc * PIECE));
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        bulk_g2s(dst + r * ROWCH, gC[r] + (long)s0 * PIECE, (uint32_t)(kc * PIECE), bar);
+        bulk_g2s(dst + STREAM + r * ROWCH, gS[r] + (long)s0 * PIECE, (uint32_t)(kc * PIECE), bar);
+      }
+    };
+    for (int ci = 0; ci < NCH - 1 && ci < nchunks; ++ci) issue(ci);
+    const uint32_t selUp = l == 0 ? 0x5454u : 0x5432u;
+    const uint32_t selDn = l == 15 ? 0x3232u : 0x5432u;
+    uint32_t L[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) L[r] = 0u;
+
+    auto step = [&](const unsigned char *pc, unsigned char *trow) {
+      uint32_t c[NR], x0[NR];
+      lds_vec<NR>(pc, c);
+      lds_vec<NR>(pc + STREAM, x0);
+      sgm_step<NR, true>(L, c, a.P1P1, a.P2P2, selUp, selDn, upper);
+      // blend: LAll = (L0 + (L1+L2+L3)) / 4 per 16-bit half (aggr.cu:192,222)
+      uint32_t la[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) la[r] = ((L[r] + x0[r]) >> 2) & 0x3fff3fffu;
+      st_vec<NR>(trow, la);
+    };
+
+    int slot = 0;
+    uint32_t parity = 0;
+    for (int ci = 0; ci < nchunks; ++ci) {
+      const int s0 = ci * K;
+      if ((s0 % W2_TS) == 0) { // entering tile t: the consumer must have released it (tile t - WTA_TILES)
+        const int t = s0 / W2_TS;
+        if (t >= WTA_TILES) mbar_wait(barEmpty + 8 * (t % WTA_TILES), (uint32_t)((t / WTA_TILES - 1) & 1));
+      }
+      mbar_wait(bar0 + 8 * slot, parity);
+      if (ci + NCH - 1 < nchunks) issue(ci + NCH - 1);
+      const int kc = min(K, steps - s0);
+      const unsigned char *pc = ring + slot * 2 * ROWCH + h * ROWCH + loff;
+      // pixel (row h, step s) of tile slot ts lies at tile row ts*32 + h*16 + s % 16
+      unsigned char *trow = tile + (((s0 / W2_TS) % WTA_TILES) * 32 + h * W2_TS + (s0 % W2_TS)) * TP + loff;
+      if (kc == K) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) { step(pc, trow); pc += PIECE; trow += TP; }
+      } else {
+        for (int k = 0; k < kc; ++k) { step(pc, trow); pc += PIECE; trow += TP; }
+      }
+      const int done = s0 + kc;
+      if ((done % W2_TS) == 0 || done == steps) { // tile complete: publish it (every lane releases its own stores)
+        const uint32_t bar = barFull + 8 * (((done - 1) / W2_TS) % WTA_TILES);
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+      }
+      if (++slot == NCH) { slot = 0; parity ^= 1; }
+    }
+    if (tr && lane == 0) tr[4 * tslot + 1] = gtimer();
+    return;
+  }
+
+  // ============================== consumer: winner-takes-all ===================================
+  uint32_t T[DPL], dconst[NR];
+#pragma unroll
+  for (int k = 0; k < DPL; ++k) T[k] = 0xffffffffu;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) dconst[r] = (uint32_t)(l * DPL + 2 * r) | ((uint32_t)(l * DPL + 2 * r + 1) << 16);
+  uint32_t *gkbuf = reinterpret_cast<uint32_t *>(wsm + lay.gk);
+  uint16_t *rbuf = reinterpret_cast<uint16_t *>(wsm + lay.rb);
+  const size_t rowpix = ((size_t)pg.n * a.rows + pg.q) * a.cols;
+  const int k100u = 100 - a.uniq;
+  const uint32_t firstmask = l == 0 ? 0xffffffffu : 0u;
+
+  auto cstep = [&](const uint32_t (&la)[NR], int k) {
+    // keys (value << 16 | d): u32 min == lowest value, then lowest d (wta.cu:30-65)
+    uint32_t key[DPL];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      key[2 * r] = __byte_perm(la[r], dconst[r], 0x1054);
+      key[2 * r + 1] = __byte_perm(la[r], dconst[r], 0x3276);
+    }
+    uint32_t lk = key[0];
+#pragma unroll
+    for (int j = 1; j < DPL; ++j) lk = min(lk, key[j]);
+    const uint32_t gk = halfwarp_min(lk, upper);
+    if (l == 0) gkbuf[h * W2_TS + k] = gk;
+    // right disparity: T_x(d) = min(T_{x-1}(d-1), key_x(d))  (wta.cu:183,190-198)
+    const uint32_t upT = __shfl_up_sync(FULL, T[DPL - 1], 1) | firstmask;
+#pragma unroll
+    for (int j = DPL - 1; j >= 1; --j) T[j] = min(T[j - 1], key[j]);
+    T[0] = min(upT, key[0]);
+    if (l == 15) rbuf[h * W2_TS + k] = (uint16_t)T[DPL - 1]; // pixel s-(D-1), stored by the tile phase
+  };
+
+  int nextseg = 0;
+  for (int t = 0; t < ntiles; ++t) {
+    const int ts = t % WTA_TILES;
+    mbar_wait(barFull + 8 * ts, (uint32_t)((t / WTA_TILES) & 1));
+    const int t0 = t * W2_TS;
+    const int cnt = min(W2_TS, steps - t0);
+    unsigned char *tbase = tile + ts * 32 * TP;
+    const unsigned char *trow = tbase + h * W2_TS * TP + loff;
+    uint32_t cur[NR], nxt[NR];
+    lds_vec<NR>(trow, cur);
+    if (cnt == W2_TS) {
+#pragma unroll
+      for (int k = 0; k < W2_TS; ++k) { // the next row's load is in flight while this one is processed
+        trow += TP;
+        if (k < W2_TS - 1) lds_vec<NR>(trow, nxt);
+        cstep(cur, k);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) cur[r] = nxt[r];
+      }
+    } else {
+      for (int k = 0; k < cnt; ++k) {
+        cstep(cur, k);
+        trow += TP;
+        if (k + 1 < cnt) lds_vec<NR>(trow, cur);
+      }
+    }
+    // one lane per pixel: lane (h, l) finishes pixel t0 + l of row h
+    __syncwarp();
+    if (l < cnt) {
+      const float disp = wta_pixel(reinterpret_cast<uint16_t *>(tbase + lane * TP), gkbuf[lane], D, k100u);
+      if (rowvalid) {
+        a.dispL[rowpix + t0 + l] = disp;
+        const int xr = t0 + l - (D - 1);
+        if (xr >= 0) a.dispR[rowpix + xr] = rbuf[lane];
+      }
+    }
+    __syncwarp();
+    {
+      const uint32_t bar = barEmpty + 8 * ts;
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+    }
+    if (nextseg < a.nseg && t0 + cnt >= a.seg_end[nextseg]) { // publish: these rows are done up to the segment end
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) atomicAdd(a.progress + nextseg, 2 * pair + 1 < npaths ? 2u : 1u);
+      ++nextseg;
+    }
+  }
+  if (rowvalid) {
+    // pixels whose diagonal leaves the image on the right: x' = cols-1-d, d < D-1
+#pragma unroll
+    for (int k = 0; k < DPL; ++k) {
+      const int d = l * DPL + k;
+      const int xp = a.cols - 1 - d;
+      if (d < D - 1 && xp >= 0) a.dispR[rowpix + xp] = (uint16_t)(T[k] & 0xffffu);
+    }
+  }
+  if (tr && lane == 0) tr[4 * tslot + 3] = gtimer();
+}
+
+static int g_wta_pairs = 1; // experiment switch (ssb_debug_set_wta_pairs)
 template <int NR> struct AggrCfg {
   static constexpr int K0 = 32 / NR < 2 ? 2 : 32 / NR;
   template <int MODE> static constexpr int K() { return MODE == 1 ? (K0 >= 4 ? K0 / 2 : K0) : K0; }
@@ -797,6 +1050,30 @@ static cudaError_t launch_one(const AggrArgs &a_in, cudaStream_t st) {
   cudaError_t e;
   if constexpr (MODE == 2) {
     static_assert(!PACK, "the final pass reads u16 volumes");
+    // Two rows per warp pair (aggr_wta2_kernel) where it measured faster: D = 64 in the throughput regime (C4, 256 envs:
+    // final pass 1.03 -> 0.92 ms, 58.7 -> 60.3 k env-frames/s).  It is bit-identical at D = 128 / 256 too, but slower there
+    // (C1 103 -> 137 us, C5 0.885 -> 1.12 ms: the per-register work dominates a step from NR = 2 on, and the two CREDUX of
+    // the per-half minimum lengthen the serial chain); the switch value 2 keeps those reachable for experiments.
+    if constexpr (!PARTIAL && !DBG && NR <= 4) {
+      if ((g_wta_pairs == 1 && NR == 1 && NCHO == 2) || g_wta_pairs == 2) {
+        constexpr int NR2 = 2 * NR;
+        constexpr int K2 = NR2 <= 4 ? 16 : 8;
+        constexpr int NCH2 = NCHO == 2 ? 2 : 3;
+        auto k2 = aggr_wta2_kernel<NR2, K2, NCH2>;
+        const size_t smem2 = (size_t)aggr2_smem<K2, NCH2>(a.D).total; // per pair of rows
+        const long npairs = (npaths + 1) / 2;
+        long ppb = (npairs + a.nsm - 1) / a.nsm;
+        const long fit = (long)((227 * 1024) / smem2);
+        const long cap = NR2 >= 8 ? 4 : (NCHO == 2 ? 8 : 3); // (launch bounds: 256 threads at D = 256)
+        if (ppb > cap) ppb = cap;
+        if (ppb > fit) ppb = fit;
+        if (ppb < 1) ppb = 1;
+        const size_t bsmem = smem2 * (size_t)ppb;
+        if (bsmem > 48 * 1024 && (e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem)) != cudaSuccess) return e;
+        k2<<<(unsigned)((npairs + ppb - 1) / ppb), (unsigned)(64 * ppb), bsmem, st>>>(a);
+        return cudaGetLastError();
+      }
+    }
     auto k = aggr_wta_kernel<NR, PARTIAL, DBG, K, NCH>;
     // rows per block: enough for one resident wave with one block per SM when shared memory allows
     // (<= 5 rows in the latency-bound single-frame regime; up to 8 with the 2-slot rings of the
@@ -857,6 +1134,7 @@ template <int MODE, int NCHO = 0> static cudaError_t dispatch(const AggrArgs &a,
 
 } // namespace ssb
 // debug hook (not part of include/ss_b200.h): register a device buffer of 4 * 4 * TRACE_STRIDE u64
+extern "C" void ssb_debug_set_wta_pairs(int on) { ssb::g_wta_pairs = on; }
 extern "C" int ssb_debug_set_aggr_trace(void *device_buffer) {
   return (int)cudaMemcpyToSymbol(ssb::g_trace, &device_buffer, sizeof(device_buffer));
 }

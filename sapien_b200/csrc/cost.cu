@@ -47,7 +47,7 @@ template <int BW, int BH, int TX, int NS, int TD, bool EDGE, bool PACK8, bool OD
 __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, const uint32_t *__restrict__ imR,
                                           uint16_t *__restrict__ outC, int rows, int cols, int Drt, int dbase,
                                           int xblk, int y_begin, int y_end, uint32_t *ring,
-                                          uint32_t *sLb, uint32_t *sRb, uint32_t zmask) {
+                                          uint32_t *sLb, uint32_t *sRb, uint32_t zmask, bool rb) {
   constexpr int HW = BW / 2, HH = BH / 2;
   constexpr int NH = TX + BW - 1;       // hamming columns per strip
   constexpr int DCW = 64;               // disparities per warp (32 lanes x one pair)
@@ -139,7 +139,10 @@ __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, cons
       // popc(d_lo) | popc(d_lo+1) << 16 as ONE multiply-add (fma pipe; the alu pipe is the busy one)
       asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(hv) : "r"(__popc(x1)), "r"(__popc(x0)));
       if (EDGE) { if (ib + i <= imax) hold = hv; hn[i] = hold; }
-      else hn[i] = hv;
+      else { // rb: the strip ends at the right image border, its last HW columns replicate the border column
+        if (i >= NH - HW) hv = rb ? hn[NH - 1 - HW] : hv;
+        hn[i] = hv;
+      }
     }
   };
 
@@ -221,8 +224,193 @@ __device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, cons
   }
 }
 
-template <int BW, int BH, int TX, int NS, int TD, bool PACK8, int DT>
-__global__ void __launch_bounds__(TD *NS)
+// Streaming variant of cost_band (round 2).  Same arithmetic, different schedule: instead of keeping the
+// Hamming pairs of the WHOLE current row and the WHOLE next row in registers (2 * NH of them), the
+// pairs are produced LEAD = BW-1+KA columns ahead of the sliding window and die BW columns later, so
+// only ~BW+LEAD+NH/TX of them are live at any time (the last LEAD pairs produced during a row are
+// the first ones of the next row: the stream runs across the row boundary).  The freed registers
+// buy a third block per SM (12 warps instead of 8: the kernel is latency-bound at 2 warps per
+// scheduler), the row-end copy of the next row's pairs disappears, and both running sums become one
+// three-input add per column:
+//   hs(x+1)   = hs(x) + h[x+BW] - h[x]
+//   out(y)    = out(y-1) + hs(y) - hs(y-BH)        (ring: BH slots, the slot is read, then overwritten)
+__host__ __device__ constexpr bool cost_stream_ok(int BW, int TX, int KA) {
+  const int NH = TX + BW - 1, LEAD = BW - 1 + KA;
+  if (KA < 1 || LEAD >= NH) return false;
+  // item i of the next row must be produced AFTER the last read of item i of this row (the slide of step i)
+  for (int x = 0; x < TX; ++x) {
+    const int p0 = LEAD + (x * NH) / TX, p1 = LEAD + ((x + 1) * NH) / TX;
+    for (int p = p0; p < p1; ++p)
+      if (p >= NH && x <= p - NH) return false;
+  }
+  return true;
+}
+
+template <int BW, int BH, int TX, int NS, int TD, bool EDGE, bool PACK8, bool ODD_D, int DT, int KA>
+__device__ __forceinline__ void cost_band_s(const uint32_t *__restrict__ imL, const uint32_t *__restrict__ imR,
+                                            uint16_t *__restrict__ outC, int rows, int cols, int Drt, int dbase,
+                                            int xblk, int y_begin, int y_end, uint32_t *ring,
+                                            uint32_t *sLb, uint32_t *sRb, uint32_t zmask, bool rb) {
+  constexpr int HW = BW / 2, HH = BH / 2;
+  constexpr int NH = TX + BW - 1;       // hamming columns per strip
+  constexpr int LEAD = BW - 1 + KA;     // pairs produced ahead of the window's left edge
+  constexpr bool DEPADDR = false;       // tie the staged-code loads to the chain as well (experiment)
+  static_assert(cost_stream_ok(BW, TX, KA), "look-ahead too long for this strip width");
+  constexpr int DCW = 64;               // disparities per warp (32 lanes x one pair)
+  constexpr int NRC = NH + DCW + 1;     // right census codes staged per warp
+  constexpr int SLOT = NS * TX * TD / (PACK8 ? 2 : 1); // ring words per input row
+  constexpr int XW = PACK8 ? TX / 2 : TX;              // ring words per thread and row
+  constexpr int NLL = (NH + 31) / 32, NLR = (NRC + 31) / 32;
+  constexpr int SLS = CostStage<BW, TX>::SLS, SRS = CostStage<BW, TX>::SRS;
+
+  const int D = DT ? DT : Drt;
+  const int td = threadIdx.x;
+  const int strip = threadIdx.y;
+  const int lane = td & 31;
+  const int wq = td >> 5;
+  const int d_lo = dbase + 2 * td;
+  const int dbw = dbase + DCW * wq;
+  const int xs = xblk * (NS * TX) - HW;
+  const int ib = strip * TX;
+  const int imax = cols - 1 - xs;
+  const bool live = d_lo < D;
+  if (dbw >= D) return;
+
+  int colL[NLL], colR[NLR];
+#pragma unroll
+  for (int k = 0; k < NLL; ++k) colL[k] = min(max(xs + ib + lane + 32 * k, 0), cols - 1);
+#pragma unroll
+  for (int k = 0; k < NLR; ++k) colR[k] = min(max(xs + ib + lane + 32 * k - DCW - 1 - dbw, 0), cols - 1);
+  const uint32_t sL_s = (uint32_t)__cvta_generic_to_shared(sLb), sR_s = (uint32_t)__cvta_generic_to_shared(sRb);
+  auto fetch = [&](int yin, int stage) {
+    const int yc = min(max(yin, 0), rows - 1);
+    const uint32_t *l = imL + (size_t)yc * cols;
+    const uint32_t *r = imR + (size_t)yc * cols;
+#pragma unroll
+    for (int k = 0; k < NLL; ++k)
+      if (lane + 32 * k < NH)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sL_s + 4u * (uint32_t)(stage * SLS + lane + 32 * k)), "l"(l + colL[k]) : "memory");
+#pragma unroll
+    for (int k = 0; k < NLR; ++k)
+      if (lane + 32 * k < NRC)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sR_s + 4u * (uint32_t)(stage * SRS + lane + 32 * k)), "l"(r + colR[k]) : "memory");
+  };
+  auto commit = [&]() { asm volatile("cp.async.commit_group;" ::: "memory"); };
+
+  uint32_t vacc[TX]; // vacc[x] = the last emitted sum of column x (all BH rows)
+#pragma unroll
+  for (int x = 0; x < TX; ++x) vacc[x] = 0;
+  uint32_t *myring = ring + (size_t)strip * XW * TD + td;
+  if (BH > 1) { // rows above the band read as zero
+#pragma unroll
+    for (int r = 0; r < BH; ++r)
+#pragma unroll
+      for (int x = 0; x < XW; ++x) myring[(size_t)r * SLOT + x * TD] = 0;
+  }
+  const int xo0 = xs + HW + ib;
+  char *prow = reinterpret_cast<char *>(outC) + (((size_t)y_begin * cols + xo0) * D + d_lo) * 2;
+  const size_t rowpitch = (size_t)cols * D * 2;
+  const uint32_t colpitch = (uint32_t)D * 2;
+
+  uint32_t h[NH];                                  // h[i]: Hamming pair of column i (this row, or already the next one)
+  uint32_t avn[(NH + 3) & ~3], rvn[((NH + 2) & ~1) + 2]; // staged census words; only a quad / a pair is live
+  uint32_t hold = 0;
+  // Hamming pairs of columns [i0, i1) of the row staged in `slot`, in ascending order
+  auto ham_cols = [&](int slot, uint32_t dep, int i0, int i1) {
+    const uint32_t pl = sL_s + 4u * (uint32_t)(slot * SLS) + (DEPADDR ? dep : 0u);
+    const uint32_t pr = sR_s + 4u * (uint32_t)(slot * SRS + (DCW - 2 * lane)) + (DEPADDR ? dep : 0u);
+#pragma unroll
+    for (int i = i0; i < i1; ++i) {
+      // avn / rvn persist across the calls of one row (columns come in ascending order, every row
+      // starts at column 0): a new left quad every 4 columns, a new right pair every 2
+      if ((i & 3) == 0)
+        asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(avn[i]), "=r"(avn[i + 1]), "=r"(avn[i + 2]), "=r"(avn[i + 3]) : "r"(pl + 4u * (uint32_t)i));
+      if (i == 0)
+        asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(rvn[0]), "=r"(rvn[1]) : "r"(pr));
+      if (i & 1)
+        asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(rvn[i + 1]), "=r"(rvn[i + 2]) : "r"(pr + 4u * (uint32_t)(i + 1)));
+      uint32_t x0, x1, hv;
+      asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(x0) : "r"(avn[i]), "r"(rvn[i + 1]), "r"(dep));
+      asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(x1) : "r"(avn[i]), "r"(rvn[i]), "r"(dep));
+      asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(hv) : "r"(__popc(x1)), "r"(__popc(x0)));
+      if (EDGE) {
+        if (i == 0) hold = 0;
+        if (ib + i <= imax) hold = hv;
+        h[i] = hold;
+      } else {
+        if (i >= NH - HW) hv = rb ? h[NH - 1 - HW] : hv;
+        h[i] = hv;
+      }
+    }
+  };
+  // positions [p0, p1) of the pair stream: p < NH is column p of the current row, p >= NH column p-NH of the next
+  auto produce = [&](int cslot, int nslot, uint32_t dep, int p0, int p1) {
+    if (p0 < NH) ham_cols(cslot, dep, p0, p1 < NH ? p1 : NH);
+    if (p1 > NH) ham_cols(nslot, dep, p0 > NH ? p0 - NH : 0, p1 - NH);
+  };
+
+  const int nin = (y_end - y_begin) + BH - 1;
+#pragma unroll
+  for (int s0 = 0; s0 < CSTAGES - 1; ++s0) {
+    if (s0 <= nin) fetch(y_begin - HH + s0, s0);
+    commit();
+  }
+  asm volatile("cp.async.wait_group %0;" ::"n"(CSTAGES - 2) : "memory");
+  __syncwarp();
+  ham_cols(0, 0u, 0, LEAD);
+  int wslot = 0; // ring slot of this input row: holds row it-BH until it is overwritten
+  int cslot = 0; // staging slot of input row it (row it+1 is in cslot+1)
+  for (int it = 0; it < nin; ++it) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(CSTAGES - 3) : "memory");
+    __syncwarp(); // row it+1 is visible to the whole warp, and everybody is done with row it-1's slot
+    const int nslot = cslot + 1 == CSTAGES ? 0 : cslot + 1;
+    {
+      const int fb = cslot == 0 ? CSTAGES - 1 : cslot - 1; // slot of row it-1 == slot of row it+CSTAGES-1
+      if (it + CSTAGES - 1 <= nin) fetch(y_begin - HH + it + CSTAGES - 1, fb);
+      commit();
+    }
+    const bool emit = it >= BH - 1;
+    uint32_t *rs = myring + (size_t)wslot * SLOT;
+    uint32_t hs = 0; // horizontal sum of the window of column 0
+#pragma unroll
+    for (int i = 0; i < BW; ++i) hs += h[i];
+    uint32_t hprev = 0, wold = 0, dep = 0;
+#pragma unroll
+    for (int x = 0; x < TX; ++x) {
+      produce(cslot, nslot, dep, LEAD + (x * NH) / TX, LEAD + ((x + 1) * NH) / TX);
+      if (BH > 1) {
+        uint32_t old;
+        if (!PACK8) old = rs[x * TD];
+        else if (!(x & 1)) { wold = rs[(x >> 1) * TD]; old = __byte_perm(wold, 0u, 0x4140); }
+        else old = __byte_perm(wold, 0u, 0x4342);
+        vacc[x] = vacc[x] + hs - old;
+        if (!PACK8) rs[x * TD] = hs;
+        else if (x & 1) rs[(x >> 1) * TD] = __byte_perm(hprev, hs, 0x6420);
+        else hprev = hs;
+      } else vacc[x] = hs;
+      if (live && emit && (!EDGE || xo0 + x < cols)) {
+        char *dst = prow + (uint32_t)x * colpitch;
+        if (!ODD_D) {
+          *reinterpret_cast<uint32_t *>(dst) = vacc[x];
+        } else {
+          uint16_t *d16 = reinterpret_cast<uint16_t *>(dst);
+          d16[0] = (uint16_t)(vacc[x] & 0xffffu);
+          if (d_lo + 1 < D) d16[1] = (uint16_t)(vacc[x] >> 16);
+        }
+      }
+      dep = hs & zmask;
+      if (x + 1 < TX) hs = hs + h[x + BW] - h[x]; // window of the next column
+    }
+    if (emit) prow += rowpitch;
+    wslot = wslot + 1 == BH ? 0 : wslot + 1;
+    cslot = nslot;
+  }
+}
+
+
+// KA = 0: cost_band (whole rows of pairs in registers); KA > 0: cost_band_s with KA columns of extra look-ahead
+template <int BW, int BH, int TX, int NS, int TD, bool PACK8, int DT, int KA, int MINB>
+__global__ void __launch_bounds__(TD *NS, MINB)
 cost_kernel(const uint32_t *__restrict__ cL, const uint32_t *__restrict__ cR,
             uint16_t *__restrict__ C, int rows, int cols, int D, int nchunks, int ry, uint32_t zmask) {
   constexpr int NWARP = NS * TD / 32;
@@ -240,7 +428,15 @@ cost_kernel(const uint32_t *__restrict__ cL, const uint32_t *__restrict__ cR,
   const uint32_t *imL = cL + (size_t)n * rows * cols;
   const uint32_t *imR = cR + (size_t)n * rows * cols;
   uint16_t *outC = C + (size_t)n * rows * cols * D;
-  const bool edge = (xblk + 1) * (NS * TX) + BW / 2 > cols; // needs the replicate-border hold / x bound
+  // Right image border.  When the strips tile the image (cols % TX == 0) only the LAST strip is affected, and only
+  // in its last BW/2 Hamming columns, which replicate the border column: a warp-uniform select on those (rb); strips
+  // beyond the image have nothing to do.  Otherwise the right-most block runs the EDGE variant (a per-column hold
+  // and a store bound: ~20 % more instructions, and in a one-wave grid its blocks are the tail of the kernel).
+  const bool ragged = cols % TX != 0;
+  const bool edge = ragged && (xblk + 1) * (NS * TX) + BW / 2 > cols;
+  const int xo0 = (xblk * NS + (int)threadIdx.y) * TX; // first output column of my strip
+  if (!ragged && xo0 >= cols) return;                 // warps are independent (no block barrier)
+  const bool rb = !ragged && xo0 + TX == cols;
   unsigned long long *const tr = g_cost_trace;
   const int tslot = (blockIdx.y * gridDim.x + blockIdx.x) % 8192;
   if (tr && threadIdx.x == 0 && threadIdx.y == 0) {
@@ -248,12 +444,21 @@ cost_kernel(const uint32_t *__restrict__ cL, const uint32_t *__restrict__ cR,
     asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
     tr[4 * tslot] = cost_gtimer(); tr[4 * tslot + 2] = sm;
   }
+  if constexpr (KA > 0) {
+    if (DT == 0 && (D & 1)) // odd D (generic aggregation path only): 16-bit stores, keep one slow variant
+      cost_band_s<BW, BH, TX, NS, TD, true, PACK8, true, 0, KA>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR, zmask, rb);
+    else if (edge)
+      cost_band_s<BW, BH, TX, NS, TD, true, PACK8, false, DT, KA>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR, zmask, rb);
+    else
+      cost_band_s<BW, BH, TX, NS, TD, false, PACK8, false, DT, KA>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR, zmask, rb);
+  } else {
   if (DT == 0 && (D & 1)) // odd D (generic aggregation path only): 16-bit stores, keep one slow variant
-    cost_band<BW, BH, TX, NS, TD, true, PACK8, true, 0>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR, zmask);
+    cost_band<BW, BH, TX, NS, TD, true, PACK8, true, 0>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR, zmask, rb);
   else if (edge)
-    cost_band<BW, BH, TX, NS, TD, true, PACK8, false, DT>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR, zmask);
+    cost_band<BW, BH, TX, NS, TD, true, PACK8, false, DT>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR, zmask, rb);
   else
-    cost_band<BW, BH, TX, NS, TD, false, PACK8, false, DT>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR, zmask);
+    cost_band<BW, BH, TX, NS, TD, false, PACK8, false, DT>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR, zmask, rb);
+  }
   if (tr && threadIdx.x == 0 && threadIdx.y == 0) tr[4 * tslot + 1] = cost_gtimer();
 }
 
@@ -284,10 +489,10 @@ __global__ void cost_generic_kernel(const uint32_t *__restrict__ cL, const uint3
   C[idx] = (uint16_t)acc;
 }
 
-template <int BW, int BH, int TX, int NS, int TD, bool PACK8, int DT = 0>
+template <int BW, int BH, int TX, int NS, int TD, bool PACK8, int DT = 0, int KA = 0, int MINB = 1>
 static cudaError_t launch_cfg(const uint32_t *cL, const uint32_t *cR, uint16_t *C, int N, int rows,
                               int cols, int D, cudaStream_t st) {
-  auto k = cost_kernel<BW, BH, TX, NS, TD, PACK8, DT>;
+  auto k = cost_kernel<BW, BH, TX, NS, TD, PACK8, DT, KA, MINB>;
   const size_t smem = (size_t)BH * NS * TX * TD * sizeof(uint32_t) / (PACK8 ? 2 : 1);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -310,6 +515,7 @@ static cudaError_t launch_cfg(const uint32_t *cL, const uint32_t *cR, uint16_t *
   return cudaGetLastError();
 }
 
+static int g_cost_stream = 1; // experiment switch (ssb_debug_set_cost_stream)
 template <int BW, int BH>
 static cudaError_t launch_fast(const uint32_t *cL, const uint32_t *cR, uint16_t *C, int N, int rows,
                                int cols, int D, int bits, cudaStream_t st) {
@@ -321,10 +527,15 @@ static cudaError_t launch_fast(const uint32_t *cL, const uint32_t *cR, uint16_t 
     // round 1; C4, 256 envs: 0.530 -> 0.502 ms in round 2).  That variant uses 254 registers (2 blocks = 8 warps per SM);
     // capping it at 168 or 128 registers for 12 / 16 warps measured 80 us and 113 us at C1: the kernel wants
     // instruction-level parallelism, not warps.
-    if (D == 64) return launch_cfg<BW, BH, 32, 4, 32, true, 64>(cL, cR, C, N, rows, cols, D, st);
-    if (D == 96) return launch_cfg<BW, BH, TX, 2, 64, true, 96>(cL, cR, C, N, rows, cols, D, st);
-    if (D == 128) return launch_cfg<BW, BH, 32, 2, 64, true, 128>(cL, cR, C, N, rows, cols, D, st);
-    if (D == 256) return launch_cfg<BW, BH, 32, 2, 64, true, 256>(cL, cR, C, N, rows, cols, D, st);
+    if (D == 64) return g_cost_stream ? launch_cfg<BW, BH, 32, 4, 32, true, 64, 4, 3>(cL, cR, C, N, rows, cols, D, st)
+                                      : launch_cfg<BW, BH, 32, 4, 32, true, 64>(cL, cR, C, N, rows, cols, D, st);
+    if (D == 96) return g_cost_stream ? launch_cfg<BW, BH, TX, 2, 64, true, 96, 4, 4>(cL, cR, C, N, rows, cols, D, st)
+                                      : launch_cfg<BW, BH, TX, 2, 64, true, 96>(cL, cR, C, N, rows, cols, D, st);
+    if (D == 128 && g_cost_stream == 3) return launch_cfg<BW, BH, 32, 2, 64, true, 128, 8, 3>(cL, cR, C, N, rows, cols, D, st);
+    if (D == 128) return g_cost_stream ? launch_cfg<BW, BH, 32, 2, 64, true, 128, 4, 3>(cL, cR, C, N, rows, cols, D, st)
+                                       : launch_cfg<BW, BH, 32, 2, 64, true, 128>(cL, cR, C, N, rows, cols, D, st);
+    if (D == 256) return g_cost_stream ? launch_cfg<BW, BH, 32, 2, 64, true, 256, 4, 3>(cL, cR, C, N, rows, cols, D, st)
+                                       : launch_cfg<BW, BH, 32, 2, 64, true, 256>(cL, cR, C, N, rows, cols, D, st);
   }
   if (D <= 64)
     return pack8 ? launch_cfg<BW, BH, TX, 4, 32, true>(cL, cR, C, N, rows, cols, D, st)
@@ -334,6 +545,7 @@ static cudaError_t launch_fast(const uint32_t *cL, const uint32_t *cR, uint16_t 
 }
 
 } // namespace ssb
+extern "C" void ssb_debug_set_cost_stream(int on) { ssb::g_cost_stream = on; }
 extern "C" int ssb_debug_set_cost_trace(void *device_buffer) {
   return (int)cudaMemcpyToSymbol(ssb::g_cost_trace, &device_buffer, sizeof(device_buffer));
 }
