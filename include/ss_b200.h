@@ -65,7 +65,7 @@ typedef struct {
   int32_t device;               /* CUDA device ordinal; -1 = current device                   */
   int32_t batch;                /* number of stereo pairs per compute call (>=1)              */
   int32_t keep_stages;          /* 1: also materialise L3/LAll so ss_get_stage can read them  */
-  int32_t lanes;                /* 0: automatic (2 for batch == 1 without keep_stages, else 1); 1 or 2: see ss_get_lanes */
+  int32_t lanes;                /* 0: automatic (3 for batch == 1 without keep_stages, else 1); 1, 2 or 3: see ss_get_lanes */
 } ss_config;
 
 /* E:43-55 + C:178-306.  map* / a* are host float32 [rows*cols] arrays (maps may be NULL when
@@ -160,9 +160,9 @@ int ss_get_device(const ss_engine *e, int32_t *device);
  * Passing it as the `stream` of a compute call means "the inputs are complete, no ordering".  The reference keeps
  * its three streams private (core.h:95-97). */
 int ss_get_stream(const ss_engine *e, void **stream);
-/* Extension: number of lanes.  A lane is a complete set of streams and buffers; with two, consecutive frames
- * alternate between them and overlap on the GPU (the latency-bound head and tail of one frame's kernels are filled
- * by the other frame's: C1 +15 % frames/s), results in submission order on the public stream.  Batched engines
+/* Extension: number of lanes.  A lane is a complete set of streams and buffers; with several, consecutive frames
+ * rotate over them and overlap on the GPU (the latency-bound head and tail of one frame's kernels are filled
+ * by the other frames': C1 +15 % frames/s with two, +17 % with three), results in submission order on the public stream.  Batched engines
  * fill the machine by themselves and use one lane.  Borrowed result pointers stay valid until the next compute. */
 int ss_get_lanes(const ss_engine *e, int32_t *lanes);
 

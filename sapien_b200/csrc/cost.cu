@@ -15,13 +15,14 @@
 // vertical running sum whose leaving row comes from a thread-private shared-memory ring (bytes when
 // BW * bits <= 255).  (TX+BW-1)/TX * (RY+BH-1)/RY POPC per output instead of BW*BH.
 //  * census rows reach shared memory by cp.async, CSTAGES-1 rows ahead, staged per warp with the
-//    replicate border / max(x-d,0) clamps already applied (only the right-most column block runs
-//    the EDGE variant);
+//    replicate border / max(x-d,0) clamps already applied.  The right image border costs a warp-uniform
+//    select on the last BW/2 columns of the last strip when the strips tile the image; only ragged
+//    widths run the EDGE variant (a per-column hold, ~25 % more instructions);
 //  * POPC runs on the quarter-rate xu pipe (measured 16 lanes/clk/SM, tools/ubench.cu), the sums on
-//    the alu pipe.  The row loop is software pipelined -- the Hamming pairs of row r+1 are produced
-//    column by column BETWEEN the sliding-sum steps of row r, tied to that chain through a run-time
-//    zero the compiler cannot see through -- so the two pipes overlap inside every warp instead of
-//    taking turns (phase-by-phase code measured xu time + issue time, 80 us; pipelined 69.5 us);
+//    the alu pipe.  The Hamming pairs are produced a few columns AHEAD of the sliding window, one or two
+//    per output column, tied to the sliding-sum chain through a run-time zero the compiler cannot see
+//    through -- so the two pipes overlap inside every warp instead of taking turns (phase-by-phase code
+//    measured xu time + issue time) and only ~20 pairs are live at a time (cost_band_s);
 //  * stores are 4 B per lane / 128 B per warp and every volume byte is written once.
 #include "common.cuh"
 #include "kernels.h"
@@ -43,195 +44,13 @@ template <int BW, int TX> struct CostStage { // per-warp staging buffers (words)
   static constexpr int SRS = (NH + 64 + 2 + 3) & ~3;
 };
 
-template <int BW, int BH, int TX, int NS, int TD, bool EDGE, bool PACK8, bool ODD_D, int DT>
-__device__ __forceinline__ void cost_band(const uint32_t *__restrict__ imL, const uint32_t *__restrict__ imR,
-                                          uint16_t *__restrict__ outC, int rows, int cols, int Drt, int dbase,
-                                          int xblk, int y_begin, int y_end, uint32_t *ring,
-                                          uint32_t *sLb, uint32_t *sRb, uint32_t zmask, bool rb) {
-  constexpr int HW = BW / 2, HH = BH / 2;
-  constexpr int NH = TX + BW - 1;       // hamming columns per strip
-  constexpr int DCW = 64;               // disparities per warp (32 lanes x one pair)
-  constexpr int NRC = NH + DCW + 1;     // right census codes staged per warp
-  constexpr int SLOT = NS * TX * TD / (PACK8 ? 2 : 1); // ring words per input row
-  constexpr int XW = PACK8 ? TX / 2 : TX;              // ring words per thread and row
-  constexpr int NLL = (NH + 31) / 32, NLR = (NRC + 31) / 32;
-  constexpr int SLS = CostStage<BW, TX>::SLS, SRS = CostStage<BW, TX>::SRS; // strides keep vector loads aligned
-
-  const int D = DT ? DT : Drt; // DT != 0: compile-time D, the column offsets of the stores become immediates
-  const int td = threadIdx.x; // disparity pair inside the chunk
-  const int strip = threadIdx.y;
-  const int lane = td & 31;
-  const int wq = td >> 5;               // warp inside the strip
-  const int d_lo = dbase + 2 * td;      // my disparities: d_lo, d_lo+1
-  const int dbw = dbase + DCW * wq;     // first disparity of my warp
-  const int xs = xblk * (NS * TX) - HW; // image column of block index 0
-  const int ib = strip * TX;            // block index of my first hamming column
-  const int imax = cols - 1 - xs;       // block index of the last image column (replicate border)
-  const bool live = d_lo < D;
-  if (dbw >= D) return;                 // whole warp beyond D: warps are independent (no block barrier)
-
-  // Every WARP stages the census codes of its own strip and disparity range (no __syncthreads in
-  // the row loop, so the warps of an SM drift apart and POPC bursts overlap with the other warps'
-  // sliding sums).  sL[i] = cL(clamp(xs+ib+i));  sR[j] = cR(clamp(xs+ib + j - DCW - 1 - dbw)):
-  // column i, lane l (disparity dbw + 2l) -> j = i - 2l + DCW + 1
-  int colL[NLL], colR[NLR];
-#pragma unroll
-  for (int k = 0; k < NLL; ++k) colL[k] = min(max(xs + ib + lane + 32 * k, 0), cols - 1);
-#pragma unroll
-  for (int k = 0; k < NLR; ++k) colR[k] = min(max(xs + ib + lane + 32 * k - DCW - 1 - dbw, 0), cols - 1);
-  // rows are fetched global -> shared by cp.async, CSTAGES-1 rows ahead (one commit group per row):
-  // the row loop never waits for an L2 round trip (measured: with a one-row register prefetch a
-  // warp needed ~1800 cycles per row, most of it load latency)
-  const uint32_t sL_s = (uint32_t)__cvta_generic_to_shared(sLb), sR_s = (uint32_t)__cvta_generic_to_shared(sRb);
-  auto fetch = [&](int yin, int stage) {
-    const int yc = min(max(yin, 0), rows - 1);
-    const uint32_t *l = imL + (size_t)yc * cols;
-    const uint32_t *r = imR + (size_t)yc * cols;
-#pragma unroll
-    for (int k = 0; k < NLL; ++k)
-      if (lane + 32 * k < NH)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sL_s + 4u * (uint32_t)(stage * SLS + lane + 32 * k)), "l"(l + colL[k]) : "memory");
-#pragma unroll
-    for (int k = 0; k < NLR; ++k)
-      if (lane + 32 * k < NRC)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sR_s + 4u * (uint32_t)(stage * SRS + lane + 32 * k)), "l"(r + colR[k]) : "memory");
-  };
-  auto commit = [&]() { asm volatile("cp.async.commit_group;" ::: "memory"); };
-
-  uint32_t vacc[TX];
-#pragma unroll
-  for (int x = 0; x < TX; ++x) vacc[x] = 0;
-  uint32_t *myring = ring + (size_t)strip * XW * TD + td;
-  if (BH > 1) { // the slot read in the first BH-1 rows has not been written yet: make it read as zero
-#pragma unroll
-    for (int r = 0; r < BH; ++r)
-#pragma unroll
-      for (int x = 0; x < XW; ++x) myring[(size_t)r * SLOT + x * TD] = 0;
-  }
-  // output cursor: element (y, xs+HW+ib, d_lo) of the first emitted row
-  const int xo0 = xs + HW + ib;
-  char *prow = reinterpret_cast<char *>(outC) + (((size_t)y_begin * cols + xo0) * D + d_lo) * 2;
-  const size_t rowpitch = (size_t)cols * D * 2;
-  const uint32_t colpitch = (uint32_t)D * 2;
-
-  // Hamming pairs of columns [I0, I1) of the row staged in `slot`; `dep` (always 0 at run time,
-  // opaque to the compiler) ties the group to a point of the sliding-sum chain, see below.
-  uint32_t avn[(NH + 3) & ~3], rvn[((NH + 2) & ~1) + 2]; // rvn[k] = pr[k-1]
-  uint32_t hold = 0;
-  auto ham_cols = [&](uint32_t (&hn)[NH], int slot, uint32_t dep, int i0, int i1) {
-    const uint32_t pl = sL_s + 4u * (uint32_t)(slot * SLS) + dep;                         // 16-byte aligned
-    const uint32_t pr = sR_s + 4u * (uint32_t)(slot * SRS + (DCW - 2 * lane)) + dep;      // pr[k] = rvn[k]; 8-byte aligned
-#pragma unroll
-    for (int i = i0; i < i1; ++i) {
-      // avn / rvn persist across the calls of one row (columns come in ascending order): a new
-      // left quad every 4 columns, a new right pair every 2
-      if ((i & 3) == 0)
-        asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(avn[i]), "=r"(avn[i + 1]), "=r"(avn[i + 2]), "=r"(avn[i + 3]) : "r"(pl + 4u * (uint32_t)i));
-      if (i == 0)
-        asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(rvn[0]), "=r"(rvn[1]) : "r"(pr));
-      if (i & 1) // column i needs rvn[i] (held) and rvn[i+1]: pair (rvn[i+1], rvn[i+2])
-        asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(rvn[i + 1]), "=r"(rvn[i + 2]) : "r"(pr + 4u * (uint32_t)(i + 1)));
-      // code for d_lo+1 at this column == code for d_lo one column to the left.  The third XOR
-      // input is the run-time zero that orders this POPC after the chain point it is tied to.
-      uint32_t x0, x1, hv;
-      asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(x0) : "r"(avn[i]), "r"(rvn[i + 1]), "r"(dep));
-      asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(x1) : "r"(avn[i]), "r"(rvn[i]), "r"(dep));
-      // popc(d_lo) | popc(d_lo+1) << 16 as ONE multiply-add (fma pipe; the alu pipe is the busy one)
-      asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(hv) : "r"(__popc(x1)), "r"(__popc(x0)));
-      if (EDGE) { if (ib + i <= imax) hold = hv; hn[i] = hold; }
-      else { // rb: the strip ends at the right image border, its last HW columns replicate the border column
-        if (i >= NH - HW) hv = rb ? hn[NH - 1 - HW] : hv;
-        hn[i] = hv;
-      }
-    }
-  };
-
-  const int nin = (y_end - y_begin) + BH - 1;
-  // one row more than needed is fetched (clamped): the last iteration computes a next row nobody uses
-#pragma unroll
-  for (int s0 = 0; s0 < CSTAGES - 1; ++s0) {
-    if (s0 <= nin) fetch(y_begin - HH + s0, s0);
-    commit();
-  }
-  uint32_t hc[NH], hnx[NH]; // Hamming pairs of the current / the next input row
-  asm volatile("cp.async.wait_group %0;" ::"n"(CSTAGES - 2) : "memory");
-  __syncwarp();
-  ham_cols(hc, 0, 0u, 0, NH);
-  int wslot = 0; // ring slot written by this input row; the oldest row lives in slot wslot+1 (mod BH)
-  int nslot = 1; // staging slot of input row it+1
-  // Software pipeline: while the sliding sums of row `it` run (a serial add chain, alu pipe), the
-  // Hamming pairs of row it+1 are produced (POPC, the quarter-rate xu pipe), one or two columns
-  // per output column.  Written phase by phase, every warp of an SM goes through its POPC burst
-  // and its sum phase at the same time and the two pipes take turns (measured: 80 us = xu time +
-  // issue time); interleaved per column both stay busy.
-  for (int it = 0; it < nin; ++it) {
-    asm volatile("cp.async.wait_group %0;" ::"n"(CSTAGES - 3) : "memory");
-    __syncwarp(); // row it+1 is visible to the whole warp, and everybody is done with row it-1's slot
-    {
-      const int fb = nslot >= 2 ? nslot - 2 : nslot + CSTAGES - 2; // slot of row it-1 == slot of row it+CSTAGES-1
-      if (it + CSTAGES - 1 <= nin) fetch(y_begin - HH + it + CSTAGES - 1, fb);
-      commit();
-    }
-    const bool emit = it >= BH - 1;
-    uint32_t *rs_w = myring + (size_t)wslot * SLOT;
-    const int rslot = wslot + 1 == BH ? 0 : wslot + 1;
-    const uint32_t *rs_r = myring + (size_t)rslot * SLOT;
-    uint32_t hs = 0;
-#pragma unroll
-    for (int i = 0; i < BW - 1; ++i) hs += hc[i];
-    // ring entry: the horizontal sum of this input row.  PACK8: both halves of hs are < 256
-    // (BW * census bits <= 255), so two columns share one word (bytes A.lo, A.hi, B.lo, B.hi).
-    uint32_t hprev = 0;
-    auto ring_put = [&](int x, uint32_t v) {
-      if (!PACK8) rs_w[x * TD] = v;
-      else if (x & 1) rs_w[(x >> 1) * TD] = __byte_perm(hprev, v, 0x6420);
-      else hprev = v;
-    };
-    uint32_t wold = 0;
-    auto ring_get = [&](int x) -> uint32_t {
-      if (!PACK8) return rs_r[x * TD];
-      if (!(x & 1)) { wold = rs_r[(x >> 1) * TD]; return __byte_perm(wold, 0u, 0x4140); }
-      return __byte_perm(wold, 0u, 0x4342);
-    };
-    hold = 0;
-    uint32_t dep = 0;
-#pragma unroll
-    for (int x = 0; x < TX; ++x) {
-      ham_cols(hnx, nslot, dep, (x * NH) / TX, ((x + 1) * NH) / TX);
-      hs += hc[x + BW - 1];
-      vacc[x] += hs;
-      if (BH > 1) ring_put(x, hs);
-      if (live && emit && (!EDGE || xo0 + x < cols)) {
-        char *dst = prow + (uint32_t)x * colpitch;
-        if (!ODD_D) {
-          *reinterpret_cast<uint32_t *>(dst) = vacc[x];
-        } else {
-          uint16_t *d16 = reinterpret_cast<uint16_t *>(dst);
-          d16[0] = (uint16_t)(vacc[x] & 0xffffu);
-          if (d_lo + 1 < D) d16[1] = (uint16_t)(vacc[x] >> 16);
-        }
-      }
-      hs -= hc[x];
-      dep = hs & zmask;
-      if (BH > 1) vacc[x] -= ring_get(x); // the row that leaves the window before the next input
-      else vacc[x] = 0;
-    }
-    if (emit) prow += rowpitch;
-#pragma unroll
-    for (int i = 0; i < NH; ++i) hc[i] = hnx[i];
-    wslot = wslot + 1 == BH ? 0 : wslot + 1;
-    nslot = nslot + 1 == CSTAGES ? 0 : nslot + 1;
-  }
-}
-
-// Streaming variant of cost_band (round 2).  Same arithmetic, different schedule: instead of keeping the
-// Hamming pairs of the WHOLE current row and the WHOLE next row in registers (2 * NH of them), the
-// pairs are produced LEAD = BW-1+KA columns ahead of the sliding window and die BW columns later, so
-// only ~BW+LEAD+NH/TX of them are live at any time (the last LEAD pairs produced during a row are
-// the first ones of the next row: the stream runs across the row boundary).  The freed registers
-// buy a third block per SM (12 warps instead of 8: the kernel is latency-bound at 2 warps per
-// scheduler), the row-end copy of the next row's pairs disappears, and both running sums become one
-// three-input add per column:
+// One band of rows of one strip.  The Hamming pairs are a STREAM: they are produced LEAD = BW-1+KA columns ahead
+// of the sliding window and die BW columns later, so only ~BW+LEAD+NH/TX of them are live at any time (the last
+// LEAD pairs produced during a row are the first ones of the next row: the stream runs across the row
+// boundary).  Round 1 kept the pairs of the whole current and the whole next row in registers (2 * NH of them,
+// 254 registers, 8 warps per SM, 628 instructions per row of 32 columns); the stream needs 159 registers (12
+// warps per SM: the kernel is latency-bound at 2 warps per scheduler), has no row-end copy, and both running sums
+// are one three-input add per column (524 instructions per row):
 //   hs(x+1)   = hs(x) + h[x+BW] - h[x]
 //   out(y)    = out(y-1) + hs(y) - hs(y-BH)        (ring: BH slots, the slot is read, then overwritten)
 __host__ __device__ constexpr bool cost_stream_ok(int BW, int TX, int KA) {
@@ -408,7 +227,7 @@ __device__ __forceinline__ void cost_band_s(const uint32_t *__restrict__ imL, co
 }
 
 
-// KA = 0: cost_band (whole rows of pairs in registers); KA > 0: cost_band_s with KA columns of extra look-ahead
+// KA: columns of extra look-ahead of the Hamming-pair stream; MINB: resident blocks per SM the register budget is sized for
 template <int BW, int BH, int TX, int NS, int TD, bool PACK8, int DT, int KA, int MINB>
 __global__ void __launch_bounds__(TD *NS, MINB)
 cost_kernel(const uint32_t *__restrict__ cL, const uint32_t *__restrict__ cR,
@@ -444,21 +263,12 @@ cost_kernel(const uint32_t *__restrict__ cL, const uint32_t *__restrict__ cR,
     asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
     tr[4 * tslot] = cost_gtimer(); tr[4 * tslot + 2] = sm;
   }
-  if constexpr (KA > 0) {
-    if (DT == 0 && (D & 1)) // odd D (generic aggregation path only): 16-bit stores, keep one slow variant
-      cost_band_s<BW, BH, TX, NS, TD, true, PACK8, true, 0, KA>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR, zmask, rb);
-    else if (edge)
-      cost_band_s<BW, BH, TX, NS, TD, true, PACK8, false, DT, KA>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR, zmask, rb);
-    else
-      cost_band_s<BW, BH, TX, NS, TD, false, PACK8, false, DT, KA>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR, zmask, rb);
-  } else {
   if (DT == 0 && (D & 1)) // odd D (generic aggregation path only): 16-bit stores, keep one slow variant
-    cost_band<BW, BH, TX, NS, TD, true, PACK8, true, 0>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR, zmask, rb);
+    cost_band_s<BW, BH, TX, NS, TD, true, PACK8, true, 0, KA>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR, zmask, rb);
   else if (edge)
-    cost_band<BW, BH, TX, NS, TD, true, PACK8, false, DT>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR, zmask, rb);
+    cost_band_s<BW, BH, TX, NS, TD, true, PACK8, false, DT, KA>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR, zmask, rb);
   else
-    cost_band<BW, BH, TX, NS, TD, false, PACK8, false, DT>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR, zmask, rb);
-  }
+    cost_band_s<BW, BH, TX, NS, TD, false, PACK8, false, DT, KA>(imL, imR, outC, rows, cols, D, chunk * 2 * TD, xblk, y_begin, y_end, ring, sL, sR, zmask, rb);
   if (tr && threadIdx.x == 0 && threadIdx.y == 0) tr[4 * tslot + 1] = cost_gtimer();
 }
 
@@ -489,7 +299,7 @@ __global__ void cost_generic_kernel(const uint32_t *__restrict__ cL, const uint3
   C[idx] = (uint16_t)acc;
 }
 
-template <int BW, int BH, int TX, int NS, int TD, bool PACK8, int DT = 0, int KA = 0, int MINB = 1>
+template <int BW, int BH, int TX, int NS, int TD, bool PACK8, int DT = 0, int KA = 4, int MINB = 1>
 static cudaError_t launch_cfg(const uint32_t *cL, const uint32_t *cR, uint16_t *C, int N, int rows,
                               int cols, int D, cudaStream_t st) {
   auto k = cost_kernel<BW, BH, TX, NS, TD, PACK8, DT, KA, MINB>;
@@ -515,7 +325,6 @@ static cudaError_t launch_cfg(const uint32_t *cL, const uint32_t *cR, uint16_t *
   return cudaGetLastError();
 }
 
-static int g_cost_stream = 1; // experiment switch (ssb_debug_set_cost_stream)
 template <int BW, int BH>
 static cudaError_t launch_fast(const uint32_t *cL, const uint32_t *cR, uint16_t *C, int N, int rows,
                                int cols, int D, int bits, cudaStream_t st) {
@@ -523,19 +332,14 @@ static cudaError_t launch_fast(const uint32_t *cL, const uint32_t *cR, uint16_t 
   // a BW-wide Hamming sum fits one byte: half-size ring (BH == 1 reads back the word it is writing)
   const bool pack8 = BH > 1 && BW * bits <= 255;
   if constexpr (BW == 7 && BH == 7) if (pack8) { // the stock block size: compile-time D for the usual disparity ranges
-    // TX = 32 everywhere but D = 96: 38/32 instead of 22/16 Hamming columns per output column (C1 73.6 -> 69.5 us in
-    // round 1; C4, 256 envs: 0.530 -> 0.502 ms in round 2).  That variant uses 254 registers (2 blocks = 8 warps per SM);
-    // capping it at 168 or 128 registers for 12 / 16 warps measured 80 us and 113 us at C1: the kernel wants
-    // instruction-level parallelism, not warps.
-    if (D == 64) return g_cost_stream ? launch_cfg<BW, BH, 32, 4, 32, true, 64, 4, 3>(cL, cR, C, N, rows, cols, D, st)
-                                      : launch_cfg<BW, BH, 32, 4, 32, true, 64>(cL, cR, C, N, rows, cols, D, st);
-    if (D == 96) return g_cost_stream ? launch_cfg<BW, BH, TX, 2, 64, true, 96, 4, 4>(cL, cR, C, N, rows, cols, D, st)
-                                      : launch_cfg<BW, BH, TX, 2, 64, true, 96>(cL, cR, C, N, rows, cols, D, st);
-    if (D == 128 && g_cost_stream == 3) return launch_cfg<BW, BH, 32, 2, 64, true, 128, 8, 3>(cL, cR, C, N, rows, cols, D, st);
-    if (D == 128) return g_cost_stream ? launch_cfg<BW, BH, 32, 2, 64, true, 128, 4, 3>(cL, cR, C, N, rows, cols, D, st)
-                                       : launch_cfg<BW, BH, 32, 2, 64, true, 128>(cL, cR, C, N, rows, cols, D, st);
-    if (D == 256) return g_cost_stream ? launch_cfg<BW, BH, 32, 2, 64, true, 256, 4, 3>(cL, cR, C, N, rows, cols, D, st)
-                                       : launch_cfg<BW, BH, 32, 2, 64, true, 256>(cL, cR, C, N, rows, cols, D, st);
+    // 32 columns per thread (38/32 instead of 22/16 Hamming columns per output column) where the strips tile the usual
+    // image widths; D = 96 is the 848-column sensor (848 % 32 = 16 would put every right-most block on the EDGE path).
+    // 159 registers -> three blocks (12 warps) per SM; D = 96: 118 registers, four blocks.  (Two blocks per SM with the
+    // same schedule: C1 stage 62 -> 66 us; frame rate with three lanes and the C5 sweep with two pipelines unchanged.)
+    if (D == 64) return launch_cfg<BW, BH, 32, 4, 32, true, 64, 4, 3>(cL, cR, C, N, rows, cols, D, st);
+    if (D == 96) return launch_cfg<BW, BH, TX, 2, 64, true, 96, 4, 4>(cL, cR, C, N, rows, cols, D, st);
+    if (D == 128) return launch_cfg<BW, BH, 32, 2, 64, true, 128, 4, 3>(cL, cR, C, N, rows, cols, D, st);
+    if (D == 256) return launch_cfg<BW, BH, 32, 2, 64, true, 256, 4, 3>(cL, cR, C, N, rows, cols, D, st);
   }
   if (D <= 64)
     return pack8 ? launch_cfg<BW, BH, TX, 4, 32, true>(cL, cR, C, N, rows, cols, D, st)
@@ -545,7 +349,6 @@ static cudaError_t launch_fast(const uint32_t *cL, const uint32_t *cR, uint16_t 
 }
 
 } // namespace ssb
-extern "C" void ssb_debug_set_cost_stream(int on) { ssb::g_cost_stream = on; }
 extern "C" int ssb_debug_set_cost_trace(void *device_buffer) {
   return (int)cudaMemcpyToSymbol(ssb::g_cost_trace, &device_buffer, sizeof(device_buffer));
 }

@@ -1048,14 +1048,15 @@ static int core_get_launches_per_compute(Core *e, int32_t *count) {
 }
 
 // =====================================================================================================================
-// The public engine: one or two LANES behind the C ABI.
+// The public engine: up to three LANES behind the C ABI.
 //
 // A lane (Core) owns a complete set of streams and buffers.  Single frames of one stereo pair leave every kernel with
 // a latency-bound head and tail (a 720-row pass cannot fill 148 SMs evenly; the final pass is a serial chain per row),
-// and kernels of one stream run back to back, so with ONE lane those phases add up.  With two lanes consecutive
-// frames alternate between two independent stream sets and the tail of one frame's kernel is filled by the other
-// frame's kernels: C1 1 954 -> 2 252 frames/s with device inputs (tools/pipe_experiment.py, round 2), bit-identical
-// results.  Batched engines (many environments per call) already fill the machine and gain nothing: they get one lane.
+// and kernels of one stream run back to back, so with ONE lane those phases add up.  With several lanes consecutive
+// frames rotate over independent stream sets and the tail of one frame's kernel is filled by the other frames'
+// kernels: C1 1 954 (one lane) -> 2 250 (two) -> 2 285 (three) frames/s with device inputs (tools/hook_ab.py
+// ssb_debug_set_auto_lanes, round 2), bit-identical results; a lane costs four cost volumes of memory (1 GB at C1).
+// Batched engines (many environments per call) already fill the machine and gain nothing: they get one lane.
 //
 // The engine's PUBLIC stream (ss_get_stream) runs no kernels: it waits, in submission order, for the end of every
 // frame, so work enqueued on it after compute() sees that frame (and all earlier ones).  A frame starts only after the
@@ -1063,29 +1064,34 @@ static int core_get_launches_per_compute(Core *e, int32_t *count) {
 // last used its lane -- which keeps "borrowed result pointer + stream order" safe without serialising the lanes.
 // =====================================================================================================================
 struct ss_engine {
-  Core *lane[2] = {nullptr, nullptr};
+  static constexpr int MAXL = 3;
+  Core *lane[MAXL] = {nullptr, nullptr, nullptr};
   int nlanes = 1;
   int last = 0;          // lane of the most recent frame
   uint64_t frames = 0;   // frames enqueued so far
   int device = 0;
   bool profiling = false; // stage times are measured with the frames of ONE lane running alone
   cudaStream_t pub = nullptr;
-  cudaEvent_t ev_join = nullptr, ev_tail[2] = {nullptr, nullptr};
-  struct Ticket { uint64_t pub = 0, sub = 0; int lane = 0; } tk[4];
+  cudaEvent_t ev_join = nullptr, ev_tail[MAXL] = {nullptr, nullptr, nullptr};
+  struct Ticket { uint64_t pub = 0, sub = 0; int lane = 0; } tk[8];
 
   int next_lane() const { return (profiling || nlanes == 1) ? 0 : (int)(frames % (uint64_t)nlanes); }
 };
 
 namespace {
 
+int g_auto_lanes = 3; // lanes of a single-pair engine created with lanes = 0 (ssb_debug_set_auto_lanes: A/B hook, tools/hook_ab.py)
+
 // before a frame is enqueued on `lane`: order it after the public stream as it was when the previous frame was enqueued
 int lane_begin(ss_engine *e, int lane) {
-  if (e->frames > 0) CK(cudaStreamWaitEvent(e->lane[lane]->stream, e->ev_tail[(e->frames - 1) & 1], 0));
+  // (frame k reuses the lane of frame k - nlanes: it waits for the public stream as it was when frame k - nlanes + 1 was enqueued)
+  const uint64_t back = (uint64_t)std::max(e->nlanes - 1, 1);
+  if (e->frames >= back) CK(cudaStreamWaitEvent(e->lane[lane]->stream, e->ev_tail[(e->frames - back) % ss_engine::MAXL], 0));
   return SS_OK;
 }
 // after a frame has been enqueued on `lane`: the public stream completes behind it
 int lane_end(ss_engine *e, int lane) {
-  CK(cudaEventRecord(e->ev_tail[e->frames & 1], e->pub)); // (the public stream BEFORE this frame's join)
+  CK(cudaEventRecord(e->ev_tail[e->frames % ss_engine::MAXL], e->pub)); // (the public stream BEFORE this frame's join)
   CK(cudaEventRecord(e->ev_join, e->lane[lane]->stream));
   CK(cudaStreamWaitEvent(e->pub, e->ev_join, 0));
   e->last = lane;
@@ -1099,7 +1105,7 @@ int create_lanes(const ss_config *cfg, const ss_calibration *cal, const float *m
                  const float *mapRy, const float *a1, const float *a2, const float *a3, ss_engine **out) {
   if (!cfg || !out) return fail(SS_ERR_INVALID, "null argument");
   *out = nullptr;
-  if (cfg->lanes < 0 || cfg->lanes > 2) return fail(SS_ERR_INVALID, "lanes must be 0 (automatic), 1 or 2");
+  if (cfg->lanes < 0 || cfg->lanes > ss_engine::MAXL) return fail(SS_ERR_INVALID, "lanes must be 0 (automatic), 1, 2 or 3");
   ss_engine *e = new ss_engine();
   auto make = [&](Core **c) {
     return cal ? core_create_calibrated(cfg, cal, c) : core_create(cfg, mapLx, mapLy, mapRx, mapRy, a1, a2, a3, c);
@@ -1107,15 +1113,17 @@ int create_lanes(const ss_config *cfg, const ss_calibration *cal, const float *m
   int r = make(&e->lane[0]);
   if (r) { delete e; return r; }
   e->device = e->lane[0]->device;
-  const int want = cfg->lanes ? cfg->lanes : ((cfg->batch == 1 && !cfg->keep_stages) ? 2 : 1);
-  if (want == 2) {
+  const int want = cfg->lanes ? cfg->lanes : ((cfg->batch == 1 && !cfg->keep_stages) ? g_auto_lanes : 1);
+  if (want >= 2) {
     ss_config c2 = *cfg;
     c2.device = e->device;
     const ss_config *saved = cfg;
     cfg = &c2;
     const std::string keep = g_err;
-    if (make(&e->lane[1]) == SS_OK) e->nlanes = 2; // (no memory for a second lane: one lane, silently)
-    else { e->lane[1] = nullptr; g_err = keep; cudaGetLastError(); }
+    for (int i = 1; i < want; ++i) {
+      if (make(&e->lane[i]) == SS_OK) e->nlanes = i + 1; // (no memory for another lane: fewer lanes, silently)
+      else { e->lane[i] = nullptr; g_err = keep; cudaGetLastError(); break; }
+    }
     cfg = saved;
   }
   DeviceGuard g(e->device);
@@ -1131,6 +1139,7 @@ int create_lanes(const ss_config *cfg, const ss_calibration *cal, const float *m
 
 extern "C" {
 
+void ssb_debug_set_auto_lanes(int n) { g_auto_lanes = n < 1 ? 1 : (n > ss_engine::MAXL ? ss_engine::MAXL : n); }
 const char *ss_last_error(void) { return g_err.c_str(); }
 const char *ss_version(void) { return "ss_b200 0.2 (sm_100a)"; }
 
@@ -1203,12 +1212,12 @@ int ss_submit_host_u8(ss_engine *e, const uint8_t *left, const uint8_t *right, c
   uint64_t sub = 0;
   const uint64_t mine = e ? e->frames + 1 : 0;
   SS_FRAME((r = core_submit_host_u8(c, left, right, bbox, out_host, capacity_bytes, &sub),
-            r ? r : (e->tk[mine & 3] = {mine, sub, ln}, *ticket = mine, 0)))
+            r ? r : (e->tk[mine & 7] = {mine, sub, ln}, *ticket = mine, 0)))
 }
 int ss_wait_frame(ss_engine *e, uint64_t ticket) {
   if (!e) return fail(SS_ERR_INVALID, "null engine");
   if (ticket == 0 || ticket > e->frames) return fail(SS_ERR_INVALID, "unknown frame ticket");
-  const ss_engine::Ticket &t = e->tk[ticket & 3];
+  const ss_engine::Ticket &t = e->tk[ticket & 7];
   if (t.pub != ticket) return SS_OK; // an old ticket: the lanes' in-flight limit has already waited for that frame
   return core_wait_frame(e->lane[t.lane], t.sub);
 }

@@ -522,6 +522,34 @@ def test_packed_path_volumes_vs_oracle(native, oracle, over):
     assert np.array_equal(batch.get_ndarray()[0].view(np.uint32), eng.get_ndarray().view(np.uint32))
 
 
+@pytest.mark.parametrize("lanes", [2, 3])
+def test_lanes_are_bit_identical_to_one_lane(native, lanes):
+    """Frames enqueued back to back rotate over the engine's lanes (independent stream / buffer sets); every frame must
+    equal what a one-lane engine computes for the same pair, for device inputs read back later and in any order."""
+    import torch
+
+    prm = configs.params("small128")
+    pairs = [configs.pair(prm, seed=900 + i) for i in range(7)]
+    solo = make_engine(native, prm, lanes=1)
+    eng = make_engine(native, prm, lanes=lanes)
+    assert eng.lanes == lanes and solo.lanes == 1
+    want = []
+    for l, r in pairs:
+        solo.compute(l, r)
+        want.append(solo.get_ndarray().copy())
+    dev = [(torch.from_numpy(synth.to_rgba(l)).cuda(), torch.from_numpy(synth.to_rgba(r)).cuda()) for l, r in pairs]
+    torch.cuda.synchronize()
+    es = torch.cuda.ExternalStream(eng.cuda_stream)
+    got = []
+    for tl, tr in dev:  # no host synchronisation between the frames: the results are cloned in stream order
+        eng.compute(tl, tr, stream=eng.cuda_stream, sync=False)
+        with torch.cuda.stream(es):
+            got.append(eng.get_cuda().torch().clone())
+    es.synchronize()
+    for i, g in enumerate(got):
+        assert np.array_equal(g.cpu().numpy().view(np.uint32), want[i].view(np.uint32)), f"frame {i} differs with {lanes} lanes"
+
+
 def test_strict_signature_results_are_never_overwritten(native):
     """compute(l, r) + get_ndarray() with nothing else: the map is delivered into a page-locked pool array which
     get_ndarray() hands out.  Arrays a caller keeps must stay intact however many frames follow (the pool only reuses

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-block timeline of the cost kernel (debug aid; needs a B200): start / end of warp 0 of every block,
-by SM, by column block and by row band, for the schedules selectable with ssb_debug_set_cost_stream."""
+by SM, by column block and by row band."""
 import ctypes, os, sys
 import numpy as np
 import torch
@@ -16,8 +16,7 @@ key = sys.argv[1] if len(sys.argv) > 1 else "C1"
 prm = configs.params(key)
 l, r = configs.pair(prm, 0)
 tl = torch.from_numpy(synth.to_rgba(l)).cuda(); tr_ = torch.from_numpy(synth.to_rgba(r)).cuda()
-for variant in [int(v) for v in (sys.argv[2:] or ["0", "1"])]:
-    lib.ssb_debug_set_cost_stream(variant)
+for variant in [0]:
     eng = simsense.DepthSensorEngine(*prm.engine_args(), device=0)
     eng.set_profiling(True)  # one lane, stages back to back
     for _ in range(3):
