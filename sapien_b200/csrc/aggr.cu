@@ -113,6 +113,9 @@ template <int NR> __device__ __forceinline__ void lds_vec(const void *p, uint32_
   } else if constexpr (NR == 2) {
     const uint2 v = *reinterpret_cast<const uint2 *>(p);
     r[0] = v.x; r[1] = v.y;
+  } else if constexpr (NR == 3) { // 12-byte lanes (D = 96 on a half-warp): three words, stride 3 -> no bank conflict
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(p);
+    r[0] = q[0]; r[1] = q[1]; r[2] = q[2];
   } else {
 #pragma unroll
     for (int i = 0; i < NR / 4; ++i) {
@@ -126,6 +129,9 @@ template <int NR> __device__ __forceinline__ void st_vec(void *p, const uint32_t
     *reinterpret_cast<uint32_t *>(p) = r[0];
   } else if constexpr (NR == 2) {
     *reinterpret_cast<uint2 *>(p) = make_uint2(r[0], r[1]);
+  } else if constexpr (NR == 3) {
+    uint32_t *q = reinterpret_cast<uint32_t *>(p);
+    q[0] = r[0]; q[1] = r[1]; q[2] = r[2];
   } else {
 #pragma unroll
     for (int i = 0; i < NR / 4; ++i)
@@ -1054,9 +1060,11 @@ static cudaError_t launch_one(const AggrArgs &a_in, cudaStream_t st) {
     // final pass 1.03 -> 0.92 ms, 58.7 -> 60.3 k env-frames/s).  It is bit-identical at D = 128 / 256 too, but slower there
     // (C1 103 -> 137 us, C5 0.885 -> 1.12 ms: the per-register work dominates a step from NR = 2 on, and the two CREDUX of
     // the per-half minimum lengthen the serial chain); the switch value 2 keeps those reachable for experiments.
-    if constexpr (!PARTIAL && !DBG && NR <= 4) {
-      if ((g_wta_pairs == 1 && NR == 1 && NCHO == 2) || g_wta_pairs == 2) {
-        constexpr int NR2 = 2 * NR;
+    if constexpr (!DBG && ((!PARTIAL && NR <= 4) || (PARTIAL && NR == 2))) {
+      // (D = 96 runs the one-row kernel with 24 of 32 lanes; on half-warps it is 16 whole lanes of 6 disparities)
+      const bool d96 = PARTIAL && a.D == 96;
+      if (PARTIAL ? (d96 && g_wta_pairs >= 1 && NCHO == 2) : ((g_wta_pairs == 1 && NR == 1 && NCHO == 2) || g_wta_pairs == 2)) {
+        constexpr int NR2 = PARTIAL ? 3 : 2 * NR;
         constexpr int K2 = NR2 <= 4 ? 16 : 8;
         constexpr int NCH2 = NCHO == 2 ? 2 : 3;
         auto k2 = aggr_wta2_kernel<NR2, K2, NCH2>;
