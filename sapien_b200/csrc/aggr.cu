@@ -843,7 +843,8 @@ __global__ void __launch_bounds__(NR >= 8 ? 256 : 512, 1) aggr_wta2_kernel(const
     const char *gC[2] = {reinterpret_cast<const char *>(a.C + pg.e0), reinterpret_cast<const char *>(a.C + pgB.e0)};
     const char *gS[2] = {reinterpret_cast<const char *>(a.aux0 + pg.e0), reinterpret_cast<const char *>(a.aux0 + pgB.e0)};
     const int nchunks = (steps + K - 1) / K;
-    auto issue = [&](int ci) { // chunk ci -> slot ci % NCH: 2 streams x 2 rows, one bulk copy each
+    auto issue = [&](int ci) { // chunk ci -> slot ci % NCH: 2 streams x 2 rows, one bulk copy each; all lanes call
+      __syncwarp(); // every lane has finished reading the slot that is refilled (the one consumed a chunk ago)
       if (lane != 0) return;
       const int slot = ci % NCH;
       const int s0 = ci * K;
