@@ -68,6 +68,8 @@ def params(name: str) -> Params:
         return _sensor_params("D435", max_disp=64, rectified=True, scale=(128, 96, 128, 96))
     if name == "small128":  # 160x96, D=128: the 32-columns-per-thread cost kernel and the 2-register SGM lanes at a sanitizer-friendly size
         return _sensor_params("D415", max_disp=128, rectified=False, roll_deg=0.5, scale=(160, 96, 240, 144))
+    if name == "small435odd":  # 128x95, D=64: an odd number of rows (x an odd batch: the last row pair of the half-warp final pass is half empty)
+        return _sensor_params("D435", max_disp=64, rectified=True, scale=(128, 95, 128, 95))
     if name == "small96":  # 144x64, D=96 (D435): the partial-lane SGM kernels and the half-warp final pass of batches
         return _sensor_params("D435", max_disp=96, rectified=True, scale=(144, 64, 144, 64))
     if name == "small256":  # 288x64, D=256

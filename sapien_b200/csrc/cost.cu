@@ -38,10 +38,11 @@ __device__ __forceinline__ unsigned long long cost_gtimer() {
 }
 
 constexpr int CSTAGES = 4; // census rows in flight per warp (cp.async ring)
-template <int BW, int TX> struct CostStage { // per-warp staging buffers (words), CSTAGES deep
+template <int BW, int TX, bool MRG = false> struct CostStage { // per-warp staging buffers (words), CSTAGES deep
   static constexpr int NH = TX + BW - 1;
-  static constexpr int SLS = (NH + 3) & ~3;
-  static constexpr int SRS = (NH + 64 + 2 + 3) & ~3;
+  // MRG (see cost_band_s): one warp serves the upper 32 disparities of TWO adjacent strips
+  static constexpr int SLS = (NH + (MRG ? TX : 0) + 3) & ~3;
+  static constexpr int SRS = (NH + (MRG ? TX : 0) + 64 + 2 + 3) & ~3;
 };
 
 // One band of rows of one strip.  The Hamming pairs are a STREAM: they are produced LEAD = BW-1+KA columns ahead
@@ -65,7 +66,12 @@ __host__ __device__ constexpr bool cost_stream_ok(int BW, int TX, int KA) {
   return true;
 }
 
-template <int BW, int BH, int TX, int NS, int TD, bool EDGE, bool PACK8, bool ODD_D, int DT, int KA>
+// MRG (D = 96, strips that tile the image): a block is three warps for two strips -- warps 0 / 1 own disparities
+// 0..63 of strip 0 / 1, warp 2 owns disparities 64..95 of BOTH strips (lanes 0-15: strip 0, lanes 16-31: strip 1)
+// instead of two half-empty warps.  Its staging buffers cover both strips (the right-image window of the second
+// strip is the first one's shifted by TX columns), every lane-dependent quantity (strip, disparity, output
+// pointer, border flag) is per lane, and the left codes are a 2-address broadcast.
+template <int BW, int BH, int TX, int NS, int TD, bool EDGE, bool PACK8, bool ODD_D, int DT, int KA, bool MRG = false>
 __device__ __forceinline__ void cost_band_s(const uint32_t *__restrict__ imL, const uint32_t *__restrict__ imR,
                                             uint16_t *__restrict__ outC, int rows, int cols, int Drt, int dbase,
                                             int xblk, int y_begin, int y_end, uint32_t *ring,
@@ -77,29 +83,40 @@ __device__ __forceinline__ void cost_band_s(const uint32_t *__restrict__ imL, co
   static_assert(cost_stream_ok(BW, TX, KA), "look-ahead too long for this strip width");
   constexpr int DCW = 64;               // disparities per warp (32 lanes x one pair)
   constexpr int NRC = NH + DCW + 1;     // right census codes staged per warp
-  constexpr int SLOT = NS * TX * TD / (PACK8 ? 2 : 1); // ring words per input row
+  static_assert(!MRG || (NS == 2 && !EDGE && !ODD_D && DT == 96), "merged upper chunks: D = 96, two strips, tiling widths");
+  constexpr int NT = MRG ? 96 : NS * TD;               // threads per block
   constexpr int XW = PACK8 ? TX / 2 : TX;              // ring words per thread and row
-  constexpr int NLL = (NH + 31) / 32, NLR = (NRC + 31) / 32;
-  constexpr int SLS = CostStage<BW, TX>::SLS, SRS = CostStage<BW, TX>::SRS;
+  constexpr int SLOT = XW * NT;                        // ring words per input row
+  constexpr int NHW = NH + (MRG ? TX : 0), NRCW = NRC + (MRG ? TX : 0); // staged per warp (the merged warp: two strips)
+  constexpr int NLL = (NHW + 31) / 32, NLR = (NRCW + 31) / 32;
+  constexpr int SLS = CostStage<BW, TX, MRG>::SLS, SRS = CostStage<BW, TX, MRG>::SRS;
 
   const int D = DT ? DT : Drt;
   const int td = threadIdx.x;
-  const int strip = threadIdx.y;
   const int lane = td & 31;
   const int wq = td >> 5;
-  const int d_lo = dbase + 2 * td;
-  const int dbw = dbase + DCW * wq;
+  const bool merged = MRG && wq == 2;                               // warp-uniform
+  const int strip = MRG ? (merged ? lane >> 4 : wq) : (int)threadIdx.y;
+  const int d_lo = MRG ? (merged ? DCW + 2 * (lane & 15) : 2 * lane) : dbase + 2 * td;
+  const int dbw = MRG ? (merged ? DCW : 0) : dbase + DCW * wq;    // first disparity of my warp
   const int xs = xblk * (NS * TX) - HW;
-  const int ib = strip * TX;
+  const int ib = strip * TX;                                        // block index of my first hamming column
+  const int ibw = merged ? 0 : ib;                                  // ... of my warp's staging buffers
   const int imax = cols - 1 - xs;
-  const bool live = d_lo < D;
+  bool live = d_lo < D;
+  if (MRG) { // (the kernel's per-strip border handling, per lane)
+    const int xo = (xblk * NS + strip) * TX;
+    live = live && xo < cols;
+    rb = xo + TX == cols;
+  }
   if (dbw >= D) return;
 
+  const int nhw = merged ? NHW : NH, nrcw = merged ? NRCW : NRC;
   int colL[NLL], colR[NLR];
 #pragma unroll
-  for (int k = 0; k < NLL; ++k) colL[k] = min(max(xs + ib + lane + 32 * k, 0), cols - 1);
+  for (int k = 0; k < NLL; ++k) colL[k] = min(max(xs + ibw + lane + 32 * k, 0), cols - 1);
 #pragma unroll
-  for (int k = 0; k < NLR; ++k) colR[k] = min(max(xs + ib + lane + 32 * k - DCW - 1 - dbw, 0), cols - 1);
+  for (int k = 0; k < NLR; ++k) colR[k] = min(max(xs + ibw + lane + 32 * k - DCW - 1 - dbw, 0), cols - 1);
   const uint32_t sL_s = (uint32_t)__cvta_generic_to_shared(sLb), sR_s = (uint32_t)__cvta_generic_to_shared(sRb);
   auto fetch = [&](int yin, int stage) {
     const int yc = min(max(yin, 0), rows - 1);
@@ -107,11 +124,11 @@ __device__ __forceinline__ void cost_band_s(const uint32_t *__restrict__ imL, co
     const uint32_t *r = imR + (size_t)yc * cols;
 #pragma unroll
     for (int k = 0; k < NLL; ++k)
-      if (lane + 32 * k < NH)
+      if (lane + 32 * k < nhw)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sL_s + 4u * (uint32_t)(stage * SLS + lane + 32 * k)), "l"(l + colL[k]) : "memory");
 #pragma unroll
     for (int k = 0; k < NLR; ++k)
-      if (lane + 32 * k < NRC)
+      if (lane + 32 * k < nrcw)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sR_s + 4u * (uint32_t)(stage * SRS + lane + 32 * k)), "l"(r + colR[k]) : "memory");
   };
   auto commit = [&]() { asm volatile("cp.async.commit_group;" ::: "memory"); };
@@ -119,12 +136,13 @@ __device__ __forceinline__ void cost_band_s(const uint32_t *__restrict__ imL, co
   uint32_t vacc[TX]; // vacc[x] = the last emitted sum of column x (all BH rows)
 #pragma unroll
   for (int x = 0; x < TX; ++x) vacc[x] = 0;
-  uint32_t *myring = ring + (size_t)strip * XW * TD + td;
+  constexpr int RS = MRG ? NT : TD; // ring stride between a thread's words (thread-private entries)
+  uint32_t *myring = MRG ? ring + td : ring + (size_t)strip * XW * TD + td;
   if (BH > 1) { // rows above the band read as zero
 #pragma unroll
     for (int r = 0; r < BH; ++r)
 #pragma unroll
-      for (int x = 0; x < XW; ++x) myring[(size_t)r * SLOT + x * TD] = 0;
+      for (int x = 0; x < XW; ++x) myring[(size_t)r * SLOT + x * RS] = 0;
   }
   const int xo0 = xs + HW + ib;
   char *prow = reinterpret_cast<char *>(outC) + (((size_t)y_begin * cols + xo0) * D + d_lo) * 2;
@@ -136,8 +154,8 @@ __device__ __forceinline__ void cost_band_s(const uint32_t *__restrict__ imL, co
   uint32_t hold = 0;
   // Hamming pairs of columns [i0, i1) of the row staged in `slot`, in ascending order
   auto ham_cols = [&](int slot, uint32_t dep, int i0, int i1) {
-    const uint32_t pl = sL_s + 4u * (uint32_t)(slot * SLS) + (DEPADDR ? dep : 0u);
-    const uint32_t pr = sR_s + 4u * (uint32_t)(slot * SRS + (DCW - 2 * lane)) + (DEPADDR ? dep : 0u);
+    const uint32_t pl = sL_s + 4u * (uint32_t)(slot * SLS + (ib - ibw)) + (DEPADDR ? dep : 0u);
+    const uint32_t pr = sR_s + 4u * (uint32_t)(slot * SRS + (DCW - 2 * (merged ? lane & 15 : lane)) + (ib - ibw)) + (DEPADDR ? dep : 0u);
 #pragma unroll
     for (int i = i0; i < i1; ++i) {
       // avn / rvn persist across the calls of one row (columns come in ascending order, every row
@@ -199,12 +217,12 @@ __device__ __forceinline__ void cost_band_s(const uint32_t *__restrict__ imL, co
       produce(cslot, nslot, dep, LEAD + (x * NH) / TX, LEAD + ((x + 1) * NH) / TX);
       if (BH > 1) {
         uint32_t old;
-        if (!PACK8) old = rs[x * TD];
-        else if (!(x & 1)) { wold = rs[(x >> 1) * TD]; old = __byte_perm(wold, 0u, 0x4140); }
+        if (!PACK8) old = rs[x * RS];
+        else if (!(x & 1)) { wold = rs[(x >> 1) * RS]; old = __byte_perm(wold, 0u, 0x4140); }
         else old = __byte_perm(wold, 0u, 0x4342);
         vacc[x] = vacc[x] + hs - old;
-        if (!PACK8) rs[x * TD] = hs;
-        else if (x & 1) rs[(x >> 1) * TD] = __byte_perm(hprev, hs, 0x6420);
+        if (!PACK8) rs[x * RS] = hs;
+        else if (x & 1) rs[(x >> 1) * RS] = __byte_perm(hprev, hs, 0x6420);
         else hprev = hs;
       } else vacc[x] = hs;
       if (live && emit && (!EDGE || xo0 + x < cols)) {
@@ -272,6 +290,24 @@ cost_kernel(const uint32_t *__restrict__ cL, const uint32_t *__restrict__ cR,
   if (tr && threadIdx.x == 0 && threadIdx.y == 0) tr[4 * tslot + 1] = cost_gtimer();
 }
 
+// D = 96 with strips that tile the image: three warps per block for two strips (cost_band_s, MRG)
+template <int BW, int BH, int TX, bool PACK8, int KA, int MINB>
+__global__ void __launch_bounds__(96, MINB)
+cost96_kernel(const uint32_t *__restrict__ cL, const uint32_t *__restrict__ cR,
+              uint16_t *__restrict__ C, int rows, int cols, int ry, uint32_t zmask) {
+  using Stage = CostStage<BW, TX, true>;
+  __shared__ __align__(16) uint32_t sLall[3 * CSTAGES * Stage::SLS];
+  __shared__ __align__(16) uint32_t sRall[3 * CSTAGES * Stage::SRS];
+  const int wib = threadIdx.x >> 5;
+  extern __shared__ uint32_t ring[]; // [BH][TX (/2)][96], thread-private entries
+  const int n = blockIdx.z;
+  const int y_begin = blockIdx.y * ry;
+  const int y_end = min(rows, y_begin + ry);
+  cost_band_s<BW, BH, TX, 2, 64, false, PACK8, false, 96, KA, true>(
+      cL + (size_t)n * rows * cols, cR + (size_t)n * rows * cols, C + (size_t)n * rows * cols * 96, rows, cols, 96, 0,
+      (int)blockIdx.x, y_begin, y_end, ring, sLall + wib * CSTAGES * Stage::SLS, sRall + wib * CSTAGES * Stage::SRS, zmask, false);
+}
+
 // Any block size: direct evaluation (bw*bh POPC per output).  Only used for block sizes that have
 // no specialisation above.
 __global__ void cost_generic_kernel(const uint32_t *__restrict__ cL, const uint32_t *__restrict__ cR,
@@ -299,6 +335,18 @@ __global__ void cost_generic_kernel(const uint32_t *__restrict__ cL, const uint3
   C[idx] = (uint16_t)acc;
 }
 
+// Rows per band.  As many bands as fit in ONE resident wave (a second, partial wave would double the kernel
+// time), at least 24 rows each so that the BH-1 warm-up rows stay a small overhead.  Grids that exceed one wave
+// anyway -- or would leave more than a fifth of it empty with whole bands (e.g. 16 environments of 848x480: 432
+// blocks for 740 slots) -- use ~64-row bands and several waves.
+static int cost_band_rows(long capacity, long columns, int rows) {
+  long bands = capacity / columns;
+  const long max_bands = (rows + 23) / 24;
+  if (bands >= max_bands) bands = max_bands;
+  else if (bands < 1 || 5 * bands * columns < 4 * capacity) bands = (rows + 63) / 64;
+  return (int)((rows + bands - 1) / bands);
+}
+
 template <int BW, int BH, int TX, int NS, int TD, bool PACK8, int DT = 0, int KA = 4, int MINB = 1>
 static cudaError_t launch_cfg(const uint32_t *cL, const uint32_t *cR, uint16_t *C, int N, int rows,
                               int cols, int D, cudaStream_t st) {
@@ -311,17 +359,27 @@ static cudaError_t launch_cfg(const uint32_t *cL, const uint32_t *cR, uint16_t *
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, TD * NS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   const int nchunks = (D + 2 * TD - 1) / (2 * TD);
   const long xb = (long)((cols + NS * TX - 1) / (NS * TX)) * nchunks;
-  // Row bands: as many as fit in ONE resident wave (a second, partial wave would double the
-  // kernel time), at least 24 rows each so that the BH-1 warm-up rows stay a small overhead.
-  // Batches that exceed one wave anyway use ~64-row bands.
   const long capacity = (long)sm_count() * per_sm;
-  long bands = capacity / (xb * N);
-  const long max_bands = (rows + 23) / 24;
-  if (bands > max_bands) bands = max_bands;
-  if (bands < 1) bands = (rows + 63) / 64;
-  const int ry = (int)((rows + bands - 1) / bands);
+  const int ry = cost_band_rows(capacity, xb * N, rows);
   dim3 grid((unsigned)xb, (unsigned)((rows + ry - 1) / ry), (unsigned)N);
   k<<<grid, dim3(TD, NS), smem, st>>>(cL, cR, C, rows, cols, D, nchunks, ry, 0u); // 0u: the opaque zero of the software pipeline
+  return cudaGetLastError();
+}
+
+template <int BW, int BH, int TX, bool PACK8, int KA, int MINB>
+static cudaError_t launch_cfg96(const uint32_t *cL, const uint32_t *cR, uint16_t *C, int N, int rows, int cols, cudaStream_t st) {
+  auto k = cost96_kernel<BW, BH, TX, PACK8, KA, MINB>;
+  const size_t smem = (size_t)BH * TX * 96 * sizeof(uint32_t) / (PACK8 ? 2 : 1);
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 96, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const long xb = (cols + 2 * TX - 1) / (2 * TX);
+  const long capacity = (long)sm_count() * per_sm;
+  const int ry = cost_band_rows(capacity, xb * N, rows);
+  dim3 grid((unsigned)xb, (unsigned)((rows + ry - 1) / ry), (unsigned)N);
+  k<<<grid, 96, smem, st>>>(cL, cR, C, rows, cols, ry, 0u);
   return cudaGetLastError();
 }
 
@@ -337,6 +395,8 @@ static cudaError_t launch_fast(const uint32_t *cL, const uint32_t *cR, uint16_t 
     // 159 registers -> three blocks (12 warps) per SM; D = 96: 118 registers, four blocks.  (Two blocks per SM with the
     // same schedule: C1 stage 62 -> 66 us; frame rate with three lanes and the C5 sweep with two pipelines unchanged.)
     if (D == 64) return launch_cfg<BW, BH, 32, 4, 32, true, 64, 4, 3>(cL, cR, C, N, rows, cols, D, st);
+    // (three warps for two strips: C3, 64 envs, cost 1.52 -> 1.24 ms; ragged widths keep four warps, two of them half empty)
+    if (D == 96 && cols % TX == 0) return launch_cfg96<BW, BH, TX, true, 4, 5>(cL, cR, C, N, rows, cols, st);
     if (D == 96) return launch_cfg<BW, BH, TX, 2, 64, true, 96, 4, 4>(cL, cR, C, N, rows, cols, D, st);
     if (D == 128) return launch_cfg<BW, BH, 32, 2, 64, true, 128, 4, 3>(cL, cR, C, N, rows, cols, D, st);
     if (D == 256) return launch_cfg<BW, BH, 32, 2, 64, true, 256, 4, 3>(cL, cR, C, N, rows, cols, D, st);

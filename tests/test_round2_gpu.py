@@ -76,6 +76,24 @@ def test_batched_device_rgba_input_vs_oracle(native, oracle, cfg, n):
         assert_depth_close(out[i], ref["out"], what=f"env {i}")
 
 
+@pytest.mark.parametrize("cfg,n", [("small435odd", 9), ("small96", 13), ("small435", 8)])
+def test_half_warp_final_pass_vs_oracle(native, oracle, cfg, n):
+    """Batches in the throughput regime (more rows than one wave of the one-row final pass holds) at D = 64 / 96 run the
+    final pass with two rows per warp pair (aggr_wta2_kernel): every environment against the oracle, including an odd
+    total number of rows (the last pair has one row) and D = 96 (16 whole lanes of 6 disparities)."""
+    prm = configs.params(cfg)
+    assert n * prm.rows > 5 * 148
+    pairs = [configs.pair(prm, seed=400 + s) for s in range(n)]
+    eng = make_engine(native, prm, batch=n)
+    for rep in range(2):  # twice: the second call reuses every ring / barrier
+        eng.compute(np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs]))
+    out = eng.get_ndarray()
+    for i, (l, r) in enumerate(pairs):
+        ref = oracle.pipeline(prm, l, r, volumes=False)
+        assert_stages_equal(eng, prm, ref, names=("disp_wta", "disp_right", "disp_med", "depth"), index=i)
+        assert_depth_close(out[i], ref["out"], what=f"env {i}")
+
+
 def test_strided_batched_camera_view(native, oracle):
     """BatchedCamera hands out [N,H,W,4] views with byte strides (batched_render_system.cpp:55-100): a view into a
     larger allocation (row pitch and env pitch larger than the packed ones) must give the same result as the packed

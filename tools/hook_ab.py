@@ -16,7 +16,7 @@ def main():
     hook = getattr(lib, sys.argv[1])
     values = [int(v) for v in sys.argv[2].split(",")]
     which = sys.argv[3:] or ["C1", "C4", "C3", "C5"]
-    batches = {"C1": 1, "C2": 1, "C4": 256, "C3": 16, "C5": 2}
+    batches = {"C1": 1, "C2": 1, "C4": 256, "C3": 64, "C5": 2}
     for key in which:
         batch = batches[key]
         prm = configs.params(key)
