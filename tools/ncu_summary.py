@@ -56,7 +56,9 @@ def launches(path):
 
 def full(paths):
     for p in paths:
-        out = subprocess.run(["ncu", "-i", p, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        # (a .csv argument is the `ncu -i X.ncu-rep --page raw --csv` page made on the GPU box: full-set reports of batched
+        #  workloads are too large to travel back)
+        out = open(p).read() if p.endswith(".csv") else subprocess.run(["ncu", "-i", p, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(out)))
         head, units, rows = rows[0], rows[1], rows[2:]
         print(f"### {p}\n")
