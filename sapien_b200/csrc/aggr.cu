@@ -532,7 +532,7 @@ __device__ __forceinline__ float wta_pixel(uint16_t *row, uint32_t gk, int D, in
 template <int NR, bool PARTIAL, bool DBG, int K, int NCH>
 // (min blocks = 1: shared memory allows one block per SM anyway, and without it ptxas caps the kernel at 64 registers
 // and spills a few; measured C4 final pass 1.070 -> 1.034 ms, C3 0.694 -> 0.688 ms, C1 / C5 unchanged)
-__global__ void __launch_bounds__(512, 1) aggr_wta_kernel(const __grid_constant__ AggrArgs a) {
+__global__ void __launch_bounds__(NR >= 4 ? 256 : 512, 1) aggr_wta_kernel(const __grid_constant__ AggrArgs a) {
   constexpr int DPL = 2 * NR;
   constexpr int NS = 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1089,7 +1089,7 @@ static cudaError_t launch_one(const AggrArgs &a_in, cudaStream_t st) {
     // batched regime, where rows are plentiful and more resident rows hide more latency)
     long ppb = (npaths + a.nsm - 1) / a.nsm;
     const long fit = (long)((227 * 1024) / smem);
-    const long cap = NCHO == 2 ? 8 : 5;
+    const long cap = NR >= 4 ? 4 : (NCHO == 2 ? 8 : 5); // (NR >= 4, i.e. D > 128: at most 3 rows fit anyway; launch bounds 256 threads, no 128-register cap)
     if (ppb > cap) ppb = cap;
     if (ppb > fit) ppb = fit;
     if (ppb < 1) ppb = 1;

@@ -377,11 +377,11 @@ cudaError_t launch_front(const FrontParams &p, cudaStream_t st) {
       // (three blocks per SM: 167 registers, no spills; four blocks = 128 registers spill a little: C4 +0.5 %, C1 +0.4 %;
       //  six / eight blocks spill more and are slower: C4 60.2 -> 58.9 / 57.4 k env-frames/s)
       else if (packed) front7_kernel<true, 3, false, false><<<grid, F7_NT, 0, st>>>(p);
-      else front7_kernel<true, 4, true, false><<<grid, F7_NT, 0, st>>>(p);
+      else front7_kernel<true, 3, true, false><<<grid, F7_NT, 0, st>>>(p);
     } else {
       if (p.cal_maps) front7_kernel<false, 3, true, true><<<grid, F7_NT, 0, st>>>(p);
-      else if (packed) front7_kernel<false, 4, false, false><<<grid, F7_NT, 0, st>>>(p);
-      else front7_kernel<false, 4, true, false><<<grid, F7_NT, 0, st>>>(p);
+      else if (packed) front7_kernel<false, 3, false, false><<<grid, F7_NT, 0, st>>>(p);
+      else front7_kernel<false, 3, true, false><<<grid, F7_NT, 0, st>>>(p);
     }
     return cudaGetLastError();
   }
