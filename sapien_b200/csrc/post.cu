@@ -118,8 +118,13 @@ __global__ void __launch_bounds__(PT_X *PT_Y) lr_median_kernel(const PostParams 
   size_t pos[NRND];
   int xs[NRND];
   bool inside[NRND];
+  // (the last round covers only NEL - (NRND-1)*NT elements -- 84 of 256 threads for the 3x3 median: warps that have no
+  //  element in a round skip it, a warp-uniform test)
+  const int wbase = tid & ~31;
 #pragma unroll
   for (int k = 0; k < NRND; ++k) {
+    inside[k] = false; xs[k] = 0; pos[k] = img; v[k] = -1.0f;
+    if (k * NT + wbase >= NEL) continue;
     const int i = min(k * NT + tid, NEL - 1);
     const int wy = i / WC, wx = i - wy * WC;
     const int y = y0 + wy - H, x = x0 + wx - H;
@@ -133,6 +138,8 @@ __global__ void __launch_bounds__(PT_X *PT_Y) lr_median_kernel(const PostParams 
     uint16_t dr[NRND];
 #pragma unroll
     for (int k = 0; k < NRND; ++k) {
+      ld[k] = 0; dr[k] = 0;
+      if (k * NT + wbase >= NEL) continue;
       ld[k] = (int)roundf(v[k]);
       dr[k] = p.dispR[pos[k] - min(max(ld[k], 0), xs[k])];
     }
