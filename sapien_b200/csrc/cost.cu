@@ -336,12 +336,12 @@ __global__ void cost_generic_kernel(const uint32_t *__restrict__ cL, const uint3
 }
 
 // Rows per band.  As many bands as fit in ONE resident wave (a second, partial wave would double the kernel
-// time), at least 24 rows each so that the BH-1 warm-up rows stay a small overhead.  Grids that exceed one wave
+// time), at least 12 rows each so that the BH-1 warm-up rows stay a bounded overhead.  Grids that exceed one wave
 // anyway -- or would leave more than a fifth of it empty with whole bands (e.g. 16 environments of 848x480: 432
 // blocks for 740 slots) -- use ~64-row bands (~128-row bands for large batches) and several waves.
 static int cost_band_rows(long capacity, long columns, int rows) {
   long bands = capacity / columns;
-  const long max_bands = (rows + 23) / 24;
+  const long max_bands = (rows + 11) / 12; // (ROI 640x360: 12-row bands 33 us, 24-row bands 37.5 us, 8-row bands 30 us; frame rate at three lanes unchanged)
   if (bands >= max_bands) bands = max_bands;
   else if (bands < 1 || 5 * bands * columns < 4 * capacity) {
     bands = (rows + 127) / 128;                                            // (6 warm-up rows per band: 128-row bands when

@@ -26,6 +26,7 @@ def main():
         if batch == 1:
             l, r = l[0], r[0]
         tl, tr = torch.from_numpy(synth.to_rgba(l)).cuda(), torch.from_numpy(synth.to_rgba(r)).cuda()
+        bb = (True, *configs.BBOX_C2) if key == "C2" else ()
         ref = None
         for on in values:
             hook(on)
@@ -33,19 +34,19 @@ def main():
             es = torch.cuda.ExternalStream(eng.cuda_stream)
             n = 40 if batch == 1 else 8
             for _ in range(5):
-                eng.compute(tl, tr, stream=eng.cuda_stream, sync=False)
+                eng.compute(tl, tr, *bb, stream=eng.cuda_stream, sync=False)
             eng.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(es)
             for _ in range(n):
-                eng.compute(tl, tr, stream=eng.cuda_stream, sync=False)
+                eng.compute(tl, tr, *bb, stream=eng.cuda_stream, sync=False)
             e1.record(es)
             es.synchronize()
             ms = e0.elapsed_time(e1) / n
             eng.set_profiling(True)
             eng.get_stage_times()
             for _ in range(n):
-                eng.compute(tl, tr, stream=eng.cuda_stream, sync=False)
+                eng.compute(tl, tr, *bb, stream=eng.cuda_stream, sync=False)
             eng.synchronize()
             st = dict(eng.get_stage_times())
             st.pop("frames", None)
