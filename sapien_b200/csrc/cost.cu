@@ -79,7 +79,6 @@ __device__ __forceinline__ void cost_band_s(const uint32_t *__restrict__ imL, co
   constexpr int HW = BW / 2, HH = BH / 2;
   constexpr int NH = TX + BW - 1;       // hamming columns per strip
   constexpr int LEAD = BW - 1 + KA;     // pairs produced ahead of the window's left edge
-  constexpr bool DEPADDR = false;       // tie the staged-code loads to the chain as well (experiment)
   static_assert(cost_stream_ok(BW, TX, KA), "look-ahead too long for this strip width");
   constexpr int DCW = 64;               // disparities per warp (32 lanes x one pair)
   constexpr int NRC = NH + DCW + 1;     // right census codes staged per warp
@@ -154,8 +153,8 @@ __device__ __forceinline__ void cost_band_s(const uint32_t *__restrict__ imL, co
   uint32_t hold = 0;
   // Hamming pairs of columns [i0, i1) of the row staged in `slot`, in ascending order
   auto ham_cols = [&](int slot, uint32_t dep, int i0, int i1) {
-    const uint32_t pl = sL_s + 4u * (uint32_t)(slot * SLS + (ib - ibw)) + (DEPADDR ? dep : 0u);
-    const uint32_t pr = sR_s + 4u * (uint32_t)(slot * SRS + (DCW - 2 * (merged ? lane & 15 : lane)) + (ib - ibw)) + (DEPADDR ? dep : 0u);
+    const uint32_t pl = sL_s + 4u * (uint32_t)(slot * SLS + (ib - ibw));
+    const uint32_t pr = sR_s + 4u * (uint32_t)(slot * SRS + (DCW - 2 * (merged ? lane & 15 : lane)) + (ib - ibw));
 #pragma unroll
     for (int i = i0; i < i1; ++i) {
       // avn / rvn persist across the calls of one row (columns come in ascending order, every row
